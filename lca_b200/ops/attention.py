@@ -1,0 +1,128 @@
+"""Block-attention dispatch: one op signature, two engines.
+
+``attn_block_fwd`` / ``attn_block_bwd`` are what every parallel algorithm in this package
+calls (ring steps, Ulysses local attention, varlen).  Engines:
+
+* ``"native"`` -- the in-tree sm_100a tcgen05/TMEM/TMA kernels (``ops/csrc/fmha_*.cu``);
+* ``"torch"``  -- :mod:`lca_b200.ops.ref_attention` (CPU/gloo, oracle, AttnType.TORCH_*).
+
+This replaces the reference's per-library wrappers with their uniform fwd/bwd contracts
+(``yunchang/kernels/attention.py:165-250``).  The contract here differs on purpose: blocks
+carry *global positions* (:class:`~lca_b200.parallel.layout.Seg` lists) so causal, sliding
+window and ALiBi are exact across ring blocks (the reference applies them per block with
+local offsets, ``ring_flash_attn.py:44``, which is only right for ``window=(-1,-1)``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, replace
+from typing import Optional, Tuple
+
+import torch
+
+from ..parallel.layout import PosSpec, Seg, pos_min_max, pos_tensor
+from . import native, ref_attention
+
+
+@dataclass(frozen=True)
+class AttnParams:
+    softmax_scale: float
+    causal: bool = False
+    window_size: Tuple[int, int] = (-1, -1)
+    softcap: float = 0.0
+    alibi_slopes: Optional[torch.Tensor] = None
+    dropout_p: float = 0.0
+    deterministic: bool = False
+
+    @staticmethod
+    def make(q, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+             alibi_slopes=None, dropout_p=0.0, deterministic=False) -> "AttnParams":
+        if softmax_scale is None:
+            softmax_scale = 1.0 / math.sqrt(q.shape[-1])
+        ws = (-1, -1) if window_size is None else (int(window_size[0]), int(window_size[1]))
+        return AttnParams(float(softmax_scale), bool(causal), ws, float(softcap or 0.0),
+                          alibi_slopes, float(dropout_p or 0.0), bool(deterministic))
+
+
+def block_is_visible(q_pos: PosSpec, k_pos: PosSpec, p: AttnParams) -> bool:
+    """False when every (q, k) pair of the block is masked -> the whole ring step is skipped.
+
+    This is the position-space generalisation of the reference's ``step <= rank`` test
+    (``ring_flash_attn.py:35``).
+    """
+    qlo, qhi = pos_min_max(q_pos)
+    klo, khi = pos_min_max(k_pos)
+    wl, wr = p.window_size
+    if p.causal and klo > qhi:
+        return False
+    if wl >= 0 and qlo - khi > wl:
+        return False
+    if wr >= 0 and not p.causal and klo - qhi > wr:
+        return False
+    return True
+
+
+def pick_engine(q: torch.Tensor, engine: Optional[str]) -> str:
+    if engine in ("torch", "native"):
+        if engine == "native" and not native.supports(q):
+            raise RuntimeError(
+                "engine='native' requested but the sm_100a extension cannot run this input "
+                f"(device={q.device}, dtype={q.dtype}, head_dim={q.shape[-1]}): {native.why_not(q)}"
+            )
+        return engine
+    if q.is_cuda:
+        if native.supports(q):
+            return "native"
+        if native.must_be_native():
+            raise RuntimeError(f"native sm_100a kernels required but unusable: {native.why_not(q)}")
+    return "torch"
+
+
+def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
+                   engine: Optional[str] = None, dropout_mask=None):
+    """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32."""
+    eng = pick_engine(q, engine)
+    if eng == "native" and p.dropout_p == 0.0:
+        return native.fmha_fwd(q, k, v, q_pos, k_pos, p)
+    return ref_attention.attn_block_fwd_ref(
+        q, k, v, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device), p.softmax_scale,
+        p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p, dropout_mask)
+
+
+def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
+                   engine: Optional[str] = None, dropout_mask=None, delta=None):
+    """-> fp32 (dq, dk, dv) contributions of this block (see ref_attention.attn_block_bwd_ref)."""
+    eng = pick_engine(q, engine)
+    if eng == "native" and p.dropout_p == 0.0 and native.has_bwd():
+        return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta)
+    return ref_attention.attn_block_bwd_ref(
+        dout, q, k, v, out, lse, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device),
+        p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p,
+        dropout_mask, delta=delta)
+
+
+# ------------------------------------------------------------------------------------------
+# online-softmax merge of partial results
+# ------------------------------------------------------------------------------------------
+def merge_out_lse_(out_acc: torch.Tensor, lse_acc: torch.Tensor, block_out: torch.Tensor,
+                   block_lse: torch.Tensor) -> None:
+    """In-place ``(out_acc, lse_acc) <- merge((out_acc, lse_acc), (block_out, block_lse))``.
+
+    out_acc ``(B,S,H,D)`` fp32, lse_acc ``(B,H,S)`` fp32; block_* same shapes (block_out any
+    float dtype).  Exact log-sum-exp merge (reference: ``yunchang/ring/utils.py:10-51``), made
+    safe for ``-inf`` rows (no visible keys so far), which the reference's sigmoid form turns
+    into NaN.
+    """
+    if out_acc.is_cuda and native.available():
+        native.merge_out_lse_(out_acc, lse_acc, block_out, block_lse)
+        return
+    new = torch.logaddexp(lse_acc, block_lse)
+    safe = torch.where(torch.isinf(new) & (new < 0), torch.zeros_like(new), new)
+    w_old = torch.exp(lse_acc - safe).transpose(1, 2).unsqueeze(-1)    # (B,S,H,1)
+    w_new = torch.exp(block_lse - safe).transpose(1, 2).unsqueeze(-1)
+    out_acc.mul_(w_old).add_(block_out.to(torch.float32) * w_new)
+    lse_acc.copy_(new)
+
+
+def with_scale(p: AttnParams, q) -> AttnParams:
+    return p if p.softmax_scale is not None else replace(p, softmax_scale=1.0 / math.sqrt(q.shape[-1]))

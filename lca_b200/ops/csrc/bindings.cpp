@@ -1,0 +1,277 @@
+// Python bindings (pybind11 via torch/extension.h) for the sm_100a kernels.
+// Host-side work done here: argument validation, CUtensorMap encoding through the driver entry
+// point (no link-time libcuda dependency, so the module imports on a CPU-only box), launching on
+// the current torch CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <torch/extension.h>
+
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "launchers.h"
+#include "symm.h"
+
+namespace lca {
+
+// ------------------------------------------------------------------------------------ tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool encode_tmap_4d(CUtensorMap* out, const void* base, int64_t D, int64_t H, int64_t S, int64_t B, int64_t stride_h,
+                    int64_t stride_s, int64_t stride_b, int box_rows, const char** err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { *err = "cuTensorMapEncodeTiled entry point unavailable"; return false; }
+  if (reinterpret_cast<uintptr_t>(base) % 16) { *err = "tensor base not 16-byte aligned"; return false; }
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(S),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(stride_h * 2), static_cast<cuuint64_t>(stride_s * 2),
+                           static_cast<cuuint64_t>(stride_b * 2)};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16) { *err = "tensor strides must be multiples of 8 elements"; return false; }
+  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 /* 16-bit payload; fp16 uses the same map */, 4,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return false; }
+  return true;
+}
+
+static void make_tmap(CUtensorMap* m, const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 4, name, " must be (B, S, H, D)");
+  TORCH_CHECK(t.stride(3) == 1, name, " last dim must be contiguous");
+  const int64_t B = t.size(0), S = t.size(1), H = t.size(2), D = t.size(3);
+  int64_t sb = t.stride(0), ss = t.stride(1), sh = t.stride(2);
+  if (B == 1) sb = S * ss;           // stride of a size-1 dim is arbitrary; keep the map valid
+  if (H == 1) sh = D;
+  const char* err = nullptr;
+  TORCH_CHECK(encode_tmap_4d(m, t.data_ptr(), D, H, S, B, sh, ss, sb, 128, &err), name, ": ", err ? err : "?");
+}
+
+static int dtype_code(const at::Tensor& t) {
+  if (t.scalar_type() == at::kFloat) return 0;
+  if (t.scalar_type() == at::kBFloat16) return 1;
+  if (t.scalar_type() == at::kHalf) return 2;
+  TORCH_CHECK(false, "unsupported dtype ", t.scalar_type());
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+
+#define LCA_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    TORCH_CHECK(_e == cudaSuccess, #expr, " failed: ", cudaGetErrorString(_e));             \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ fmha fwd
+// qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr}
+// ksegs[i] = {row0, nrows, pos0, flag}
+void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+              const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
+              int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
+              double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
+              int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit) {
+  TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda(), "q/k/v must be CUDA tensors");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(), "dtype mismatch");
+  TORCH_CHECK(out.scalar_type() == q.scalar_type() && out.stride(3) == 1, "bad out");
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.dim() == 3 && lse.stride(2) == 1, "lse must be (B,H,S) fp32");
+  const int64_t B = q.size(0), H = q.size(2), D = q.size(3), Hkv = k.size(2);
+  TORCH_CHECK(D == 64 || D == 128, "head_dim must be 64 or 128 (got ", D, ")");
+  TORCH_CHECK(k.size(3) == D && v.size(3) == D && v.size(2) == Hkv && H % Hkv == 0, "bad k/v shape");
+  TORCH_CHECK(k.size(0) == B && v.size(0) == B && v.size(1) == k.size(1), "bad k/v batch/seq");
+  TORCH_CHECK(!qsegs.empty() && qsegs.size() <= kMaxSeg && !ksegs.empty() && ksegs.size() <= kMaxSeg, "segment count");
+  TORCH_CHECK(scale > 0, "softmax_scale must be positive");
+  c10::cuda::CUDAGuard guard(q.device());
+
+  FwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  make_tmap(&p.tm_q, q, "q");
+  make_tmap(&p.tm_k, k, "k");
+  make_tmap(&p.tm_v, v, "v");
+  p.n_qseg = static_cast<int>(qsegs.size());
+  p.n_kseg = static_cast<int>(ksegs.size());
+  int64_t pairs = 0;
+  for (int i = 0; i < p.n_qseg; ++i) {
+    const auto& s = qsegs[i];
+    TORCH_CHECK(s.size() == 7, "qseg needs 7 fields");
+    TORCH_CHECK(s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= q.size(1), "qseg rows out of range");
+    p.qseg[i].row0 = static_cast<int>(s[0]);
+    p.qseg[i].nrows = static_cast<int>(s[1]);
+    p.qseg[i].pos0 = static_cast<int>(s[2]);
+    p.qseg[i].flag = static_cast<int>(s[3]);
+    p.qseg[i].o_row0 = static_cast<int>(s[4]);
+    p.qseg[i].o_base = s[5] ? reinterpret_cast<void*>(s[5]) : out.data_ptr();
+    p.qseg[i].o_sig = reinterpret_cast<uint32_t*>(s[6]);
+    if (!s[5]) TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out.size(1), "qseg output rows out of range");
+    pairs += (s[1] + 255) / 256;
+  }
+  for (int i = 0; i < p.n_kseg; ++i) {
+    const auto& s = ksegs[i];
+    TORCH_CHECK(s.size() == 4, "kseg needs 4 fields");
+    TORCH_CHECK(s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= k.size(1), "kseg rows out of range");
+    p.kseg[i].row0 = static_cast<int>(s[0]);
+    p.kseg[i].nrows = static_cast<int>(s[1]);
+    p.kseg[i].pos0 = static_cast<int>(s[2]);
+    p.kseg[i].flag = static_cast<int>(s[3]);
+  }
+  p.q_pos_stride = static_cast<int>(q_pos_stride);
+  p.k_pos_stride = static_cast<int>(k_pos_stride);
+  TORCH_CHECK(p.q_pos_stride > 0 && p.k_pos_stride > 0, "position strides must be positive");
+  p.B = static_cast<int>(B);
+  p.H = static_cast<int>(H);
+  p.Hkv = static_cast<int>(Hkv);
+  p.total_work = static_cast<int>(pairs * B * H);
+  p.wl = static_cast<int>(wl);
+  p.wr = static_cast<int>(wr);
+  p.scale = static_cast<float>(scale);
+  p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
+  p.softcap = static_cast<float>(softcap);
+  if (alibi.has_value() && alibi->defined()) {
+    const at::Tensor& a = *alibi;
+    TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat && a.is_contiguous(), "alibi_slopes must be fp32 CUDA contiguous");
+    TORCH_CHECK((a.dim() == 1 && a.size(0) == H) || (a.dim() == 2 && a.size(0) == B && a.size(1) == H), "alibi shape");
+    p.alibi = a.data_ptr<float>();
+    p.alibi_bstride = a.dim() == 2 ? static_cast<int>(H) : 0;
+  }
+  p.o_sb = out.stride(0);
+  p.o_ss = out.stride(1);
+  p.o_sh = out.stride(2);
+  TORCH_CHECK(p.o_ss % 8 == 0 && p.o_sh % 8 == 0 && (B == 1 || p.o_sb % 8 == 0), "out strides must be multiples of 8");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(out.data_ptr()) % 16 == 0, "out not 16B aligned");
+  p.o_head_off = static_cast<int>(o_head_off);
+  p.lse = lse.data_ptr<float>();
+  p.lse_sb = lse.stride(0);
+  p.lse_sh = lse.stride(1);
+  TORCH_CHECK(lse.size(0) == B && lse.size(1) == H && lse.size(2) >= q.size(1), "lse shape");
+  p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
+  p.flag_epoch = static_cast<uint32_t>(flag_epoch);
+  int sms = num_sms();
+  if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(D), q.scalar_type() == at::kBFloat16, sms,
+                              at::cuda::getCurrentCUDAStream()));
+}
+
+// ------------------------------------------------------------------------------------ utilities
+void merge_out_lse(at::Tensor& out_acc, at::Tensor& lse_acc, const at::Tensor& block_out, const at::Tensor& block_lse) {
+  TORCH_CHECK(out_acc.is_cuda() && out_acc.scalar_type() == at::kFloat && out_acc.is_contiguous() && out_acc.dim() == 4);
+  TORCH_CHECK(lse_acc.scalar_type() == at::kFloat && lse_acc.is_contiguous() && block_lse.scalar_type() == at::kFloat &&
+              block_lse.is_contiguous());
+  TORCH_CHECK(block_out.is_contiguous() && block_out.sizes() == out_acc.sizes());
+  const int B = out_acc.size(0), S = out_acc.size(1), H = out_acc.size(2), D = out_acc.size(3);
+  TORCH_CHECK(lse_acc.size(0) == B && lse_acc.size(1) == H && lse_acc.size(2) == S && block_lse.sizes() == lse_acc.sizes());
+  c10::cuda::CUDAGuard guard(out_acc.device());
+  LCA_CUDA_OK(launch_merge_out_lse(out_acc.data_ptr<float>(), lse_acc.data_ptr<float>(), block_out.data_ptr(),
+                                   dtype_code(block_out), block_lse.data_ptr<float>(), B, S, H, D,
+                                   at::cuda::getCurrentCUDAStream()));
+}
+
+at::Tensor finalize_out(const at::Tensor& out_acc, at::ScalarType dtype) {
+  TORCH_CHECK(out_acc.is_cuda() && out_acc.scalar_type() == at::kFloat && out_acc.is_contiguous());
+  TORCH_CHECK(out_acc.numel() % 4 == 0);
+  at::Tensor out = at::empty(out_acc.sizes(), out_acc.options().dtype(dtype));
+  c10::cuda::CUDAGuard guard(out_acc.device());
+  LCA_CUDA_OK(launch_finalize_out(out_acc.data_ptr<float>(), out.data_ptr(), dtype_code(out), out_acc.numel(),
+                                  at::cuda::getCurrentCUDAStream()));
+  return out;
+}
+
+at::Tensor flatten_varlen_lse(const at::Tensor& lse, const at::Tensor& cu_seqlens, int64_t total) {
+  TORCH_CHECK(lse.is_cuda() && lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.dim() == 3);
+  TORCH_CHECK(cu_seqlens.is_cuda() && cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous());
+  const int B = lse.size(0), H = lse.size(1), M = lse.size(2);
+  TORCH_CHECK(cu_seqlens.numel() == B + 1);
+  at::Tensor flat = at::empty({H, total}, lse.options());
+  c10::cuda::CUDAGuard guard(lse.device());
+  LCA_CUDA_OK(launch_flatten_lse(lse.data_ptr<float>(), flat.data_ptr<float>(), cu_seqlens.data_ptr<int>(), B, H, M,
+                                 static_cast<int>(total), at::cuda::getCurrentCUDAStream()));
+  return flat;
+}
+
+at::Tensor unflatten_varlen_lse(const at::Tensor& flat, const at::Tensor& cu_seqlens, int64_t max_seqlen) {
+  TORCH_CHECK(flat.is_cuda() && flat.scalar_type() == at::kFloat && flat.is_contiguous() && flat.dim() == 2);
+  TORCH_CHECK(cu_seqlens.is_cuda() && cu_seqlens.scalar_type() == at::kInt && cu_seqlens.is_contiguous());
+  const int H = flat.size(0), total = flat.size(1), B = cu_seqlens.numel() - 1;
+  at::Tensor pad = at::empty({B, H, max_seqlen}, flat.options());
+  c10::cuda::CUDAGuard guard(flat.device());
+  LCA_CUDA_OK(launch_unflatten_lse(flat.data_ptr<float>(), pad.data_ptr<float>(), cu_seqlens.data_ptr<int>(), B, H,
+                                   static_cast<int>(max_seqlen), total, at::cuda::getCurrentCUDAStream()));
+  return pad;
+}
+
+// (B,S,G,X...) -> (G,B,S,X...) when to_group_major, else the inverse
+at::Tensor permute_group(const at::Tensor& src, int64_t G, bool to_group_major) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous());
+  c10::cuda::CUDAGuard guard(src.device());
+  const int64_t esz = src.element_size();
+  if (to_group_major) {
+    TORCH_CHECK(src.dim() >= 4 && src.size(2) == G, "expected (B,S,G,...)");
+    const int64_t B = src.size(0), S = src.size(1);
+    const int64_t x = src.numel() / (B * S * G) * esz;
+    std::vector<int64_t> shape = {G, B, S};
+    for (int i = 3; i < src.dim(); ++i) shape.push_back(src.size(i));
+    at::Tensor dst = at::empty(shape, src.options());
+    LCA_CUDA_OK(launch_permute_heads_out(src.data_ptr(), dst.data_ptr(), B, S, G, static_cast<int>(x),
+                                         at::cuda::getCurrentCUDAStream()));
+    return dst;
+  }
+  TORCH_CHECK(src.dim() >= 4 && src.size(0) == G, "expected (G,B,S,...)");
+  const int64_t B = src.size(1), S = src.size(2);
+  const int64_t x = src.numel() / (B * S * G) * esz;
+  std::vector<int64_t> shape = {B, S, G};
+  for (int i = 3; i < src.dim(); ++i) shape.push_back(src.size(i));
+  at::Tensor dst = at::empty(shape, src.options());
+  LCA_CUDA_OK(launch_permute_heads_in(src.data_ptr(), dst.data_ptr(), B, S, G, static_cast<int>(x),
+                                      at::cuda::getCurrentCUDAStream()));
+  return dst;
+}
+
+at::Tensor attn_delta(const at::Tensor& out, const at::Tensor& dout) {
+  TORCH_CHECK(out.is_cuda() && out.dim() == 4 && out.sizes() == dout.sizes() && out.scalar_type() == dout.scalar_type());
+  TORCH_CHECK(out.stride(3) == 1 && dout.stride(3) == 1);
+  const int B = out.size(0), S = out.size(1), H = out.size(2), D = out.size(3);
+  at::Tensor delta = at::empty({B, H, S}, out.options().dtype(at::kFloat));
+  c10::cuda::CUDAGuard guard(out.device());
+  LCA_CUDA_OK(launch_delta(out.data_ptr(), dout.data_ptr(), dtype_code(out), delta.data_ptr<float>(), B, S, H, D,
+                           out.stride(0), out.stride(1), out.stride(2), dout.stride(0), dout.stride(1), dout.stride(2),
+                           at::cuda::getCurrentCUDAStream()));
+  return delta;
+}
+
+}  // namespace lca
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "lca_b200 sm_100a kernels";
+  m.def("fmha_fwd", &lca::fmha_fwd, "tcgen05 flash-attention forward (segments + global positions)");
+  m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");
+  m.def("finalize_out", &lca::finalize_out, "fp32 accumulator -> 16-bit output");
+  m.def("flatten_varlen_lse", &lca::flatten_varlen_lse);
+  m.def("unflatten_varlen_lse", &lca::unflatten_varlen_lse);
+  m.def("permute_group", &lca::permute_group);
+  m.def("attn_delta", &lca::attn_delta);
+  lca::bind_symm(m);
+  m.attr("arch") = "sm_100a";
+}

@@ -1,0 +1,55 @@
+// Host/device parameter blocks of the sm_100a attention kernels.
+//
+// Everything the kernels know about sequence parallelism arrives as *segments*: contiguous row
+// ranges of the Q / K / V tensors whose tokens sit at global positions pos0 + i*stride.  The
+// ring variants (basic / zigzag / stripe), the Ulysses gather order, sliding windows and ALiBi
+// all reduce to this description, so one kernel serves every parallel layout.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace lca {
+
+constexpr int kMaxSeg = 32;
+
+struct QSegD {
+  int row0;        // first row of the segment in the Q tensor (dim S)
+  int nrows;       // rows in the segment
+  int pos0;        // global position of row0
+  int flag;        // index into FwdParams::flags that must reach flag_epoch before Q rows are read (-1: none)
+  int o_row0;      // first destination row in the output tensor addressed by o_base
+  int pad;
+  void* o_base;    // output tensor base for this segment (may be a peer-mapped pointer)
+  uint32_t* o_sig; // optional: system-scope counter incremented once per finished 128-row tile
+};
+
+struct KSegD {
+  int row0;
+  int nrows;
+  int pos0;
+  int flag;        // index into flags (-1: none)
+};
+
+struct FwdParams {
+  CUtensorMap tm_q, tm_k, tm_v;       // 4-D (D, H, S, B) bf16/fp16, box (64, 1, 128, 1), SWIZZLE_128B
+  int n_qseg, n_kseg;
+  QSegD qseg[kMaxSeg];
+  KSegD kseg[kMaxSeg];
+  int q_pos_stride, k_pos_stride;     // position step between consecutive rows (stripe: R)
+  int B, H, Hkv;
+  int total_work;                     // sum over q segments of ceil(nrows/256) * B * H
+  int wl, wr;                         // visible iff -wl <= kpos - qpos <= wr; -1 = unbounded (causal => wr = 0)
+  float scale;                        // softmax scale
+  float scale_log2;                   // softmax scale * log2(e)
+  float softcap;                      // 0 = off
+  const float* alibi;                 // per-head slopes or nullptr
+  int alibi_bstride;                  // 0 for (H,), H for (B,H)
+  int64_t o_sb, o_ss, o_sh;           // output strides in elements (batch, row, head)
+  int o_head_off;                     // destination head index = h + o_head_off
+  float* lse;                         // (B, H, lse_rows) fp32, row index = row in the Q tensor
+  int64_t lse_sb, lse_sh;
+  const uint32_t* flags;              // arrival flags written by peers (fused paths)
+  uint32_t flag_epoch;
+};
+
+}  // namespace lca

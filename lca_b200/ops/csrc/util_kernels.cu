@@ -1,0 +1,244 @@
+// Memory-bound helper kernels (sm_100a): online-softmax merge, fp32->16-bit finalize, varlen LSE
+// flatten/unflatten, head<->sequence permutes around the NCCL all-to-all, dO.O row sums.
+//
+// Parity: yunchang/ring/utils.py:10-51 (_update_out_and_lse, TorchScript),
+//         yunchang/ring/triton_utils.py:6-137 (Triton flatten/unflatten kernels),
+//         the .contiguous() staging copies of yunchang/comm/all_to_all.py:45-49,62-65,78-100.
+// All of them are pure streaming kernels: 16-byte vector accesses, grid-stride, no smem.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include <type_traits>
+
+#include "launchers.h"
+
+namespace lca {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
+// out_acc (B,S,H,D) fp32, lse_acc (B,H,S) fp32; one thread handles 4 consecutive d of one (b,s,h).
+// The LSE is updated by the thread with d-group 0 AFTER all threads of the row have read it:
+// rows are processed by D/4 consecutive threads of one warp (D/4 <= 32 and divides 32), so a
+// __syncwarp between read and write is sufficient.
+template <typename T>
+__global__ void merge_kernel(float* __restrict__ out_acc, float* __restrict__ lse_acc,
+                             const T* __restrict__ bout, const float* __restrict__ blse, int B, int S,
+                             int H, int D) {
+  const int dg = D >> 2;
+  const int64_t nrows = static_cast<int64_t>(B) * S * H;
+  const int64_t total = nrows * dg;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t start = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // all threads of a warp iterate the same number of times (total padded to warp multiple below)
+  const int64_t total_pad = (total + 31) / 32 * 32;
+  for (int64_t i = start; i < total_pad; i += step) {
+    const bool live = i < total;
+    const int64_t rowi = live ? i / dg : 0;
+    const int g = live ? static_cast<int>(i - rowi * dg) : 1;
+    const int h = static_cast<int>(rowi % H);
+    const int64_t bs = rowi / H;
+    const int s = static_cast<int>(bs % S);
+    const int b = static_cast<int>(bs / S);
+    const int64_t li = (static_cast<int64_t>(b) * H + h) * S + s;
+    float w_old = 0.f, w_new = 0.f, lnew = 0.f;
+    if (live) {
+      const float la = lse_acc[li];
+      const float lb = blse[li];
+      const float mx = fmaxf(la, lb);
+      if (mx == -INFINITY) {
+        lnew = -INFINITY;
+      } else {
+        const float ea = __expf(la - mx), eb = __expf(lb - mx);
+        const float sum = ea + eb;
+        lnew = mx + __logf(sum);
+        w_old = ea / sum;
+        w_new = eb / sum;
+      }
+      float4 a = *reinterpret_cast<const float4*>(out_acc + rowi * D + g * 4);
+      float bx, by, bz, bw;
+      if constexpr (sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(bout + rowi * D + g * 4);
+        bx = t.x; by = t.y; bz = t.z; bw = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(bout + rowi * D + g * 4);
+        const T* e = reinterpret_cast<const T*>(&t);
+        bx = to_f(e[0]); by = to_f(e[1]); bz = to_f(e[2]); bw = to_f(e[3]);
+      }
+      a.x = a.x * w_old + bx * w_new;
+      a.y = a.y * w_old + by * w_new;
+      a.z = a.z * w_old + bz * w_new;
+      a.w = a.w * w_old + bw * w_new;
+      *reinterpret_cast<float4*>(out_acc + rowi * D + g * 4) = a;
+    }
+    __syncwarp();
+    if (live && g == 0) lse_acc[li] = lnew;
+  }
+}
+
+template <typename T>
+__global__ void finalize_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t n4) {
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += step) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i * 4);
+    if constexpr (sizeof(T) == 2) {
+      T o[4];
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        o[0] = __float2bfloat16_rn(a.x); o[1] = __float2bfloat16_rn(a.y);
+        o[2] = __float2bfloat16_rn(a.z); o[3] = __float2bfloat16_rn(a.w);
+      } else {
+        o[0] = __float2half_rn(a.x); o[1] = __float2half_rn(a.y);
+        o[2] = __float2half_rn(a.z); o[3] = __float2half_rn(a.w);
+      }
+      *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<uint2*>(o);
+    } else {
+      *reinterpret_cast<float4*>(dst + i * 4) = a;
+    }
+  }
+}
+
+// padded (B,H,max_s) -> flat (H,total) and back; grid (ceil(max_s/128), B, H)
+__global__ void flatten_lse_kernel(const float* __restrict__ pad, float* __restrict__ flat,
+                                   const int* __restrict__ cu, int H, int max_s, int total) {
+  const int b = blockIdx.y, h = blockIdx.z;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int beg = cu[b], len = cu[b + 1] - beg;
+  if (s < len) flat[static_cast<int64_t>(h) * total + beg + s] = pad[(static_cast<int64_t>(b) * H + h) * max_s + s];
+}
+__global__ void unflatten_lse_kernel(const float* __restrict__ flat, float* __restrict__ pad,
+                                     const int* __restrict__ cu, int H, int max_s, int total) {
+  const int b = blockIdx.y, h = blockIdx.z;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int beg = cu[b], len = cu[b + 1] - beg;
+  if (s < max_s)
+    pad[(static_cast<int64_t>(b) * H + h) * max_s + s] = s < len ? flat[static_cast<int64_t>(h) * total + beg + s] : -INFINITY;
+}
+
+// src (B,S,G,X) -> dst (G,B,S,X), X = chunk of `xv` 16-byte vectors (or the inverse with kOut=false)
+template <bool kOut>
+__global__ void permute_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t BS, int G, int xv) {
+  const int64_t total = BS * G * xv;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += step) {
+    const int x = static_cast<int>(i % xv);
+    const int64_t r = i / xv;
+    const int g = static_cast<int>(r % G);
+    const int64_t bs = r / G;
+    const int64_t j = (static_cast<int64_t>(g) * BS + bs) * xv + x;   // index in (G,BS,X)
+    if (kOut) dst[j] = src[i]; else dst[i] = src[j];
+  }
+}
+
+// delta[b,h,s] = sum_d out[b,s,h,d] * dout[b,s,h,d]; one warp per (b,s,h)
+template <typename T>
+__global__ void delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
+                             int B, int S, int H, int D, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                             int64_t d_sb, int64_t d_ss, int64_t d_sh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nrows = static_cast<int64_t>(B) * S * H;
+  const int64_t wstep = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < nrows; r += wstep) {
+    const int h = static_cast<int>(r % H);
+    const int64_t bs = r / H;
+    const int s = static_cast<int>(bs % S);
+    const int b = static_cast<int>(bs / S);
+    const T* o = out + b * o_sb + s * o_ss + h * o_sh;
+    const T* g = dout + b * d_sb + s * d_ss + h * d_sh;
+    float acc = 0.f;
+    for (int d = lane * 8; d < D; d += 256) {
+      const uint4 a = *reinterpret_cast<const uint4*>(o + d);
+      const uint4 c = *reinterpret_cast<const uint4*>(g + d);
+      const T* ea = reinterpret_cast<const T*>(&a);
+      const T* ec = reinterpret_cast<const T*>(&c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += to_f(ea[k]) * to_f(ec[k]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * S + s] = acc;
+  }
+}
+
+inline int grid_for(int64_t work_items, int threads) {
+  int64_t g = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace
+
+cudaError_t launch_merge_out_lse(float* out_acc, float* lse_acc, const void* block_out, int block_dtype,
+                                 const float* block_lse, int B, int S, int H, int D, cudaStream_t stream) {
+  if (D % 4 != 0 || D / 4 > 32 || 32 % (D / 4) != 0) return cudaErrorInvalidValue;  // one row per <= warp
+  const int64_t total = static_cast<int64_t>(B) * S * H * (D / 4);
+  const int threads = 256;
+  const int grid = grid_for(total, threads);
+  if (block_dtype == 0)
+    merge_kernel<float><<<grid, threads, 0, stream>>>(out_acc, lse_acc, static_cast<const float*>(block_out), block_lse, B, S, H, D);
+  else if (block_dtype == 1)
+    merge_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(out_acc, lse_acc, static_cast<const __nv_bfloat16*>(block_out), block_lse, B, S, H, D);
+  else
+    merge_kernel<__half><<<grid, threads, 0, stream>>>(out_acc, lse_acc, static_cast<const __half*>(block_out), block_lse, B, S, H, D);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize_out(const float* out_acc, void* out, int out_dtype, int64_t n, cudaStream_t stream) {
+  const int64_t n4 = n / 4;
+  const int threads = 256;
+  const int grid = grid_for(n4, threads);
+  if (out_dtype == 1) finalize_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(out_acc, static_cast<__nv_bfloat16*>(out), n4);
+  else if (out_dtype == 2) finalize_kernel<__half><<<grid, threads, 0, stream>>>(out_acc, static_cast<__half*>(out), n4);
+  else finalize_kernel<float><<<grid, threads, 0, stream>>>(out_acc, static_cast<float*>(out), n4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flatten_lse(const float* pad, float* flat, const int* cu, int B, int H, int max_s, int total, cudaStream_t stream) {
+  dim3 grid((max_s + 127) / 128, B, H);
+  flatten_lse_kernel<<<grid, 128, 0, stream>>>(pad, flat, cu, H, max_s, total);
+  return cudaGetLastError();
+}
+cudaError_t launch_unflatten_lse(const float* flat, float* pad, const int* cu, int B, int H, int max_s, int total, cudaStream_t stream) {
+  dim3 grid((max_s + 127) / 128, B, H);
+  unflatten_lse_kernel<<<grid, 128, 0, stream>>>(flat, pad, cu, H, max_s, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_permute_heads_out(const void* src, void* dst, int B, int S, int G, int x_bytes, cudaStream_t stream) {
+  if (x_bytes % 16) return cudaErrorInvalidValue;
+  const int64_t BS = static_cast<int64_t>(B) * S;
+  const int xv = x_bytes / 16;
+  permute_kernel<true><<<grid_for(BS * G * xv, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), BS, G, xv);
+  return cudaGetLastError();
+}
+cudaError_t launch_permute_heads_in(const void* src, void* dst, int B, int S, int G, int x_bytes, cudaStream_t stream) {
+  if (x_bytes % 16) return cudaErrorInvalidValue;
+  const int64_t BS = static_cast<int64_t>(B) * S;
+  const int xv = x_bytes / 16;
+  permute_kernel<false><<<grid_for(BS * G * xv, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), BS, G, xv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* delta, int B, int S, int H, int D,
+                         int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t d_sb, int64_t d_ss, int64_t d_sh,
+                         cudaStream_t stream) {
+  if (D % 8) return cudaErrorInvalidValue;
+  const int64_t nrows = static_cast<int64_t>(B) * S * H;
+  const int threads = 256;
+  const int grid = grid_for(nrows * 32, threads);
+  if (dtype == 1)
+    delta_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
+  else
+    delta_kernel<__half><<<grid, threads, 0, stream>>>(static_cast<const __half*>(out), static_cast<const __half*>(dout), delta, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
+  return cudaGetLastError();
+}
+
+}  // namespace lca

@@ -1,0 +1,162 @@
+"""Loader and thin Python wrappers for the in-tree sm_100a extension (``lca_b200/ops/_C*.so``).
+
+Policy: on a machine with a Blackwell GPU the CUDA path is THE path -- if the extension is
+missing or fails to import we raise (no silent eager fallback), unless the user explicitly opts
+out with ``LCA_B200_ALLOW_FALLBACK=1``.  On CPU-only hosts everything routes to the torch engine.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ..parallel.layout import PosSpec, Seg
+
+_C = None
+_LOAD_ERROR: Optional[str] = None
+SUPPORTED_HEAD_DIMS = (64, 128)
+
+
+def _load():
+    global _C, _LOAD_ERROR
+    if _C is not None or _LOAD_ERROR is not None:
+        return _C
+    try:
+        _C = importlib.import_module("lca_b200.ops._C")
+    except Exception as e:  # noqa: BLE001
+        _LOAD_ERROR = f"{type(e).__name__}: {e}"
+        _C = None
+    return _C
+
+
+def ext():
+    c = _load()
+    if c is None:
+        raise RuntimeError(
+            f"lca_b200 native extension not loadable ({_LOAD_ERROR}); build it with "
+            "`python -m lca_b200.ops.build`"
+        )
+    return c
+
+
+def _is_blackwell(device) -> bool:
+    try:
+        major, _ = torch.cuda.get_device_capability(device)
+    except Exception:  # noqa: BLE001
+        return False
+    return major == 10
+
+
+def available() -> bool:
+    """Extension importable and a sm_100 device visible."""
+    if not torch.cuda.is_available():
+        return False
+    return _load() is not None and _is_blackwell(torch.cuda.current_device())
+
+
+def must_be_native() -> bool:
+    """On a Blackwell box the native path is mandatory unless explicitly waived."""
+    if os.environ.get("LCA_B200_ALLOW_FALLBACK", "0") == "1":
+        return False
+    return torch.cuda.is_available() and _is_blackwell(torch.cuda.current_device())
+
+
+def why_not(q: torch.Tensor) -> str:
+    if not q.is_cuda:
+        return "tensor is not on CUDA"
+    if _load() is None:
+        return f"extension not loadable: {_LOAD_ERROR}"
+    if not _is_blackwell(q.device):
+        return "device is not sm_100"
+    if q.dtype not in (torch.bfloat16, torch.float16):
+        return f"dtype {q.dtype} (need bf16/fp16)"
+    if q.shape[-1] not in SUPPORTED_HEAD_DIMS:
+        return f"head_dim {q.shape[-1]} (supported: {SUPPORTED_HEAD_DIMS})"
+    return ""
+
+
+def supports(q: torch.Tensor) -> bool:
+    return why_not(q) == ""
+
+
+def has_bwd() -> bool:
+    c = _load()
+    return c is not None and hasattr(c, "fmha_bwd")
+
+
+# ------------------------------------------------------------------------------------------
+def _common_stride(spec: PosSpec) -> int:
+    strides = {s.stride for s in spec if s.count > 1}
+    if len(strides) > 1:
+        raise ValueError(f"segments with different position strides: {spec}")
+    return strides.pop() if strides else 1
+
+
+def _rows(spec: PosSpec) -> List[Tuple[int, int, int]]:
+    """-> [(row0, nrows, pos0)]"""
+    out, off = [], 0
+    for s in spec:
+        if s.count > 0:
+            out.append((off, s.count, s.start))
+        off += s.count
+    return out
+
+
+def window_bounds(p) -> Tuple[int, int]:
+    wl, wr = p.window_size
+    if p.causal:
+        wr = 0 if wr < 0 else min(wr, 0)
+    return int(wl), int(wr)
+
+
+def _tma_ready(t: torch.Tensor) -> torch.Tensor:
+    """TMA needs: last dim contiguous, other strides multiples of 8 elements, 16B-aligned base."""
+    ok = t.stride(-1) == 1 and all(st % 8 == 0 for st in t.stride()[:-1]) and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+def fmha_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p, out=None, lse=None, sm_limit: int = 0):
+    """Forward attention of one block with global-position masks.  -> (out, lse)."""
+    C = ext()
+    q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
+    B, Sq, H, D = q.shape
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+    if lse is None:
+        lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    # heaviest (latest) segments first: the kernel walks q segments in the given order
+    qrows = sorted(_rows(q_pos), key=lambda r: -r[2])
+    qsegs = [[r0, n, pos0, -1, r0, 0, 0] for (r0, n, pos0) in qrows]
+    ksegs = [[r0, n, pos0, -1] for (r0, n, pos0) in _rows(k_pos)]
+    wl, wr = window_bounds(p)
+    alibi = p.alibi_slopes
+    if alibi is not None:
+        alibi = alibi.to(device=q.device, dtype=torch.float32).contiguous()
+    C.fmha_fwd(q, k, v, qsegs, ksegs, _common_stride(q_pos), _common_stride(k_pos), out, 0, lse,
+               float(p.softmax_scale), wl, wr, float(p.softcap), alibi, 0, 0, int(sm_limit))
+    return out, lse
+
+
+def fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=None):
+    raise NotImplementedError("native backward not built yet")
+
+
+def merge_out_lse_(out_acc, lse_acc, block_out, block_lse) -> None:
+    D = out_acc.shape[-1]
+    if D % 4 == 0 and D // 4 <= 32 and 32 % (D // 4) == 0 and out_acc.is_contiguous() and lse_acc.is_contiguous():
+        ext().merge_out_lse(out_acc, lse_acc, block_out.contiguous(), block_lse.contiguous())
+    else:  # odd head dims: same math in torch
+        new = torch.logaddexp(lse_acc, block_lse)
+        safe = torch.where(torch.isinf(new) & (new < 0), torch.zeros_like(new), new)
+        w_old = torch.exp(lse_acc - safe).transpose(1, 2).unsqueeze(-1)
+        w_new = torch.exp(block_lse - safe).transpose(1, 2).unsqueeze(-1)
+        out_acc.mul_(w_old).add_(block_out.to(torch.float32) * w_new)
+        lse_acc.copy_(new)
+
+
+def finalize_out(out_acc: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if out_acc.is_cuda and available() and out_acc.is_contiguous() and out_acc.numel() % 4 == 0:
+        return ext().finalize_out(out_acc, dtype)
+    return out_acc.to(dtype)
