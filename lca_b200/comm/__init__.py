@@ -1,0 +1,8 @@
+"""``yunchang.comm``-compatible namespace (``comm/__init__.py``)."""
+from ..parallel.all_to_all import SeqAllToAll4D, SeqAllToAll5D, all_to_all_4D, all_to_all_5D
+from ..parallel.layout import (EXTRACT_FUNC_DICT, basic_extract_local, gather_global, local_token_index,
+                               stripe_extract_local, zigzag_extract_local)
+
+__all__ = ["SeqAllToAll4D", "SeqAllToAll5D", "all_to_all_4D", "all_to_all_5D", "EXTRACT_FUNC_DICT",
+           "basic_extract_local", "stripe_extract_local", "zigzag_extract_local", "gather_global",
+           "local_token_index"]

@@ -1,0 +1,76 @@
+"""Kernel selection API, name-compatible with ``yunchang.kernels`` (``kernels/__init__.py:38-295``).
+
+On B200 there is exactly one production attention engine -- the in-tree tcgen05 kernels -- so the
+15-member ``AttnType`` enum of the reference is kept for source compatibility and mapped as:
+
+=====================  ==============================================================
+AttnType               engine here
+=====================  ==============================================================
+FA, FA3, FLASHINFER    native sm_100a tcgen05 kernel (torch oracle on CPU)
+SAGE_* / SPARSE_SAGE   native kernel (bf16/fp16 math; quantised variants are future work)
+TORCH / TORCH_*        pure-PyTorch engine with a TRUE log-sum-exp (CPU capable)
+AITER, NPU             other vendors' hardware -> ValueError
+=====================  ==============================================================
+
+``AttnType.TORCH`` (value ``"torch"``) exists because the reference's own benchmark offers
+``--attn_type torch`` although its enum has no such member.
+"""
+from __future__ import annotations
+
+from enum import Enum
+
+import torch
+
+from .attention import (flash_attn_backward, flash_attn_forward, flash_attn_func,
+                        pytorch_attn_backward, pytorch_attn_forward, pytorch_attn_func)
+
+
+class AttnType(Enum):
+    AITER = "aiter"
+    FA = "fa"
+    FA3 = "fa3"
+    FLASHINFER = "flashinfer"
+    TORCH = "torch"
+    TORCH_MATH = "torch_math"
+    TORCH_FLASH = "torch_flash"
+    TORCH_EFFICIENT = "torch_efficient"
+    TORCH_CUDNN = "torch_cudnn"
+    SAGE_AUTO = "sage_auto"
+    SAGE_FP16 = "sage_fp16"
+    SAGE_FP16_TRITON = "sage_fp16_triton"
+    SAGE_FP8 = "sage_fp8"
+    SAGE_FP8_SM90 = "sage_fp8_sm90"
+    SPARSE_SAGE = "sparse_sage"
+    NPU = "npu"
+
+    @classmethod
+    def from_string(cls, s: str):
+        for member in cls:
+            if member.value == s:
+                return member
+        raise ValueError(f"'{s}' is not a valid {cls.__name__}")
+
+
+_FOREIGN = {AttnType.AITER: "AMD ROCm (aiter)", AttnType.NPU: "Ascend NPU"}
+
+
+def is_torch_type(t) -> bool:
+    return isinstance(t, AttnType) and t.value.startswith("torch")
+
+
+def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_processor: torch.nn.Module = None):
+    """Return a callable for ``stage`` in {"fwd-only", "bwd-only", "fwd-bwd"} (``kernels/__init__.py:63-65``)."""
+    if impl_type in _FOREIGN:
+        raise ValueError(f"AttnType.{impl_type.name} targets {_FOREIGN[impl_type]}; not available in the B200 build")
+    if stage not in ("fwd-only", "bwd-only", "fwd-bwd"):
+        raise ValueError(f"Unknown stage: {stage}")
+    torch_like = is_torch_type(impl_type)
+    if stage == "fwd-only":
+        return pytorch_attn_forward if torch_like else flash_attn_forward
+    if stage == "bwd-only":
+        return pytorch_attn_backward if torch_like else flash_attn_backward
+    return pytorch_attn_func if torch_like else flash_attn_func
+
+
+__all__ = ["AttnType", "select_flash_attn_impl", "flash_attn_forward", "flash_attn_backward", "flash_attn_func",
+           "pytorch_attn_forward", "pytorch_attn_backward", "pytorch_attn_func"]

@@ -20,7 +20,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ..parallel.layout import PosSpec, Seg, pos_min_max, pos_tensor
+from ..parallel.layout import PosSpec, Seg, group_tensor, has_groups, pos_min_max, pos_tensor
 from . import native, ref_attention
 
 
@@ -50,16 +50,22 @@ def block_is_visible(q_pos: PosSpec, k_pos: PosSpec, p: AttnParams) -> bool:
     This is the position-space generalisation of the reference's ``step <= rank`` test
     (``ring_flash_attn.py:35``).
     """
-    qlo, qhi = pos_min_max(q_pos)
-    klo, khi = pos_min_max(k_pos)
     wl, wr = p.window_size
-    if p.causal and klo > qhi:
-        return False
-    if wl >= 0 and qlo - khi > wl:
-        return False
-    if wr >= 0 and not p.causal and klo - qhi > wr:
-        return False
-    return True
+    for g in {s.group for s in q_pos}:
+        qs = tuple(s for s in q_pos if s.group == g and s.count > 0)
+        ks = tuple(s for s in k_pos if s.group == g and s.count > 0)
+        if not qs or not ks:
+            continue
+        qlo, qhi = pos_min_max(qs)
+        klo, khi = pos_min_max(ks)
+        if p.causal and klo > qhi:
+            continue
+        if wl >= 0 and qlo - khi > wl:
+            continue
+        if wr >= 0 and not p.causal and klo - qhi > wr:
+            continue
+        return True
+    return False
 
 
 def pick_engine(q: torch.Tensor, engine: Optional[str]) -> str:
@@ -84,9 +90,12 @@ def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
     eng = pick_engine(q, engine)
     if eng == "native" and p.dropout_p == 0.0:
         return native.fmha_fwd(q, k, v, q_pos, k_pos, p)
+    grp = has_groups(q_pos) or has_groups(k_pos)
     return ref_attention.attn_block_fwd_ref(
         q, k, v, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device), p.softmax_scale,
-        p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p, dropout_mask)
+        p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p, dropout_mask,
+        q_grp=group_tensor(q_pos, q.device) if grp else None,
+        k_grp=group_tensor(k_pos, q.device) if grp else None)
 
 
 def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
@@ -98,7 +107,9 @@ def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: A
     return ref_attention.attn_block_bwd_ref(
         dout, q, k, v, out, lse, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device),
         p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p,
-        dropout_mask, delta=delta)
+        dropout_mask, delta=delta,
+        q_grp=group_tensor(q_pos, q.device) if (has_groups(q_pos) or has_groups(k_pos)) else None,
+        k_grp=group_tensor(k_pos, q.device) if (has_groups(q_pos) or has_groups(k_pos)) else None)
 
 
 # ------------------------------------------------------------------------------------------

@@ -87,8 +87,8 @@ static int num_sms() {
   } while (0)
 
 // ------------------------------------------------------------------------------------ fmha fwd
-// qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr}
-// ksegs[i] = {row0, nrows, pos0, flag}
+// qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr, group}
+// ksegs[i] = {row0, nrows, pos0, flag, group}
 void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
               const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
               int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
@@ -117,7 +117,7 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
   int64_t pairs = 0;
   for (int i = 0; i < p.n_qseg; ++i) {
     const auto& s = qsegs[i];
-    TORCH_CHECK(s.size() == 7, "qseg needs 7 fields");
+    TORCH_CHECK(s.size() == 8, "qseg needs 8 fields");
     TORCH_CHECK(s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= q.size(1), "qseg rows out of range");
     p.qseg[i].row0 = static_cast<int>(s[0]);
     p.qseg[i].nrows = static_cast<int>(s[1]);
@@ -126,17 +126,19 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
     p.qseg[i].o_row0 = static_cast<int>(s[4]);
     p.qseg[i].o_base = s[5] ? reinterpret_cast<void*>(s[5]) : out.data_ptr();
     p.qseg[i].o_sig = reinterpret_cast<uint32_t*>(s[6]);
+    p.qseg[i].group = static_cast<int>(s[7]);
     if (!s[5]) TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out.size(1), "qseg output rows out of range");
     pairs += (s[1] + 255) / 256;
   }
   for (int i = 0; i < p.n_kseg; ++i) {
     const auto& s = ksegs[i];
-    TORCH_CHECK(s.size() == 4, "kseg needs 4 fields");
+    TORCH_CHECK(s.size() == 5, "kseg needs 5 fields");
     TORCH_CHECK(s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= k.size(1), "kseg rows out of range");
     p.kseg[i].row0 = static_cast<int>(s[0]);
     p.kseg[i].nrows = static_cast<int>(s[1]);
     p.kseg[i].pos0 = static_cast<int>(s[2]);
     p.kseg[i].flag = static_cast<int>(s[3]);
+    p.kseg[i].group = static_cast<int>(s[4]);
   }
   p.q_pos_stride = static_cast<int>(q_pos_stride);
   p.k_pos_stride = static_cast<int>(k_pos_stride);

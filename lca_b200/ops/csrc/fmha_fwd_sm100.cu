@@ -86,7 +86,7 @@ __device__ __forceinline__ int sched_work(int round) {
 // Deterministic enumeration of the K/V tiles a Q pair has to visit (identical in every role).
 struct TileIter {
   int seg, kt;
-  int qmin, qmax;
+  int qmin, qmax, qgroup;
   // current tile
   int k_row0, nvalid, kpos0, flag;
   __device__ __forceinline__ void init(const FwdParams& p, const Work& wk) {
@@ -94,11 +94,12 @@ struct TileIter {
     kt = -1;
     qmin = wk.pos0;
     qmax = wk.pos0 + (wk.nrows - 1) * p.q_pos_stride;
+    qgroup = p.qseg[wk.qseg].group;
   }
   __device__ __forceinline__ bool next(const FwdParams& p) {
     while (seg < p.n_kseg) {
       const KSegD s = p.kseg[seg];
-      const int nt = (s.nrows + BN - 1) / BN;
+      const int nt = (s.group == qgroup) ? (s.nrows + BN - 1) / BN : 0;
       while (++kt < nt) {
         const int r0 = kt * BN;
         const int nv = min(BN, s.nrows - r0);

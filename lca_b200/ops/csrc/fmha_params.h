@@ -18,7 +18,7 @@ struct QSegD {
   int pos0;        // global position of row0
   int flag;        // index into FwdParams::flags that must reach flag_epoch before Q rows are read (-1: none)
   int o_row0;      // first destination row in the output tensor addressed by o_base
-  int pad;
+  int group;       // attention group id: a Q segment only visits K segments of the same group (varlen)
   void* o_base;    // output tensor base for this segment (may be a peer-mapped pointer)
   uint32_t* o_sig; // optional: system-scope counter incremented once per finished 128-row tile
 };
@@ -28,6 +28,7 @@ struct KSegD {
   int nrows;
   int pos0;
   int flag;        // index into flags (-1: none)
+  int group;
 };
 
 struct FwdParams {

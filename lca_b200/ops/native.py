@@ -94,14 +94,17 @@ def _common_stride(spec: PosSpec) -> int:
     return strides.pop() if strides else 1
 
 
-def _rows(spec: PosSpec) -> List[Tuple[int, int, int]]:
-    """-> [(row0, nrows, pos0)]"""
+def _rows(spec: PosSpec) -> List[Tuple[int, int, int, int]]:
+    """-> [(row0, nrows, pos0, group)]"""
     out, off = [], 0
     for s in spec:
         if s.count > 0:
-            out.append((off, s.count, s.start))
+            out.append((off, s.count, s.start, s.group))
         off += s.count
     return out
+
+
+MAX_SEG = 32
 
 
 def window_bounds(p) -> Tuple[int, int]:
@@ -128,15 +131,43 @@ def fmha_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p, out=None, lse=None, sm_
         lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
     # heaviest (latest) segments first: the kernel walks q segments in the given order
     qrows = sorted(_rows(q_pos), key=lambda r: -r[2])
-    qsegs = [[r0, n, pos0, -1, r0, 0, 0] for (r0, n, pos0) in qrows]
-    ksegs = [[r0, n, pos0, -1] for (r0, n, pos0) in _rows(k_pos)]
+    krows = _rows(k_pos)
     wl, wr = window_bounds(p)
     alibi = p.alibi_slopes
     if alibi is not None:
         alibi = alibi.to(device=q.device, dtype=torch.float32).contiguous()
-    C.fmha_fwd(q, k, v, qsegs, ksegs, _common_stride(q_pos), _common_stride(k_pos), out, 0, lse,
-               float(p.softmax_scale), wl, wr, float(p.softcap), alibi, 0, 0, int(sm_limit))
+    qs, ks = _common_stride(q_pos), _common_stride(k_pos)
+    # the kernel takes <= MAX_SEG segments per side; many-sequence varlen batches are issued in
+    # chunks of whole groups (each launch writes disjoint output rows)
+    for qchunk, kchunk in _chunk_by_group(qrows, krows):
+        qsegs = [[r0, n, pos0, -1, r0, 0, 0, g] for (r0, n, pos0, g) in qchunk]
+        ksegs = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in kchunk]
+        C.fmha_fwd(q, k, v, qsegs, ksegs, qs, ks, out, 0, lse, float(p.softmax_scale), wl, wr,
+                   float(p.softcap), alibi, 0, 0, int(sm_limit))
     return out, lse
+
+
+def _chunk_by_group(qrows, krows):
+    if len(qrows) <= MAX_SEG and len(krows) <= MAX_SEG:
+        yield qrows, krows
+        return
+    groups = sorted({r[3] for r in qrows})
+    cur_q, cur_k = [], []
+    for g in groups:
+        gq = [r for r in qrows if r[3] == g]
+        gk = [r for r in krows if r[3] == g]
+        if len(gq) > MAX_SEG or len(gk) > MAX_SEG:
+            raise ValueError("a single attention group has more than 32 segments")
+        if not gk:
+            gk = []
+        if len(cur_q) + len(gq) > MAX_SEG or len(cur_k) + len(gk) > MAX_SEG:
+            if cur_q and cur_k:
+                yield cur_q, cur_k
+            cur_q, cur_k = [], []
+        cur_q += gq
+        cur_k += gk
+    if cur_q and cur_k:
+        yield cur_q, cur_k
 
 
 def fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=None):

@@ -23,15 +23,18 @@ import torch
 NEG_INF = float("-inf")
 
 
-def _bias_and_mask(q_pos, k_pos, causal, window_size, alibi_slopes, H, device):
+def _bias_and_mask(q_pos, k_pos, causal, window_size, alibi_slopes, H, device, q_grp=None, k_grp=None):
     """-> (mask (Sq,Sk) bool or None [True = masked], bias (H,Sq,Sk) fp32 or None)."""
     wl, wr = window_size
     mask = None
     rel = None
+    if q_grp is not None and k_grp is not None:
+        mask = q_grp.view(-1, 1) != k_grp.view(1, -1)
     if causal or wl >= 0 or wr >= 0 or alibi_slopes is not None:
         rel = k_pos.view(1, -1) - q_pos.view(-1, 1)  # (Sq, Sk), k - q
     if causal:
-        mask = rel > 0
+        m = rel > 0
+        mask = m if mask is None else (mask | m)
     if wl >= 0:
         m = rel < -wl
         mask = m if mask is None else (mask | m)
@@ -71,6 +74,8 @@ def attn_block_fwd_ref(
     dropout_p: float = 0.0,
     dropout_mask: Optional[torch.Tensor] = None,
     q_chunk: int = 2048,
+    q_grp: Optional[torch.Tensor] = None,
+    k_grp: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
@@ -85,7 +90,8 @@ def attn_block_fwd_ref(
         s = torch.matmul(qf, kf) * softmax_scale                # (B,H,sq,Sk)
         if softcap > 0:
             s = softcap * torch.tanh(s / softcap)
-        mask, bias = _bias_and_mask(q_pos[s0:s1], k_pos, causal, window_size, alibi_slopes, H, dev)
+        mask, bias = _bias_and_mask(q_pos[s0:s1], k_pos, causal, window_size, alibi_slopes, H, dev,
+                                    None if q_grp is None else q_grp[s0:s1], k_grp)
         if bias is not None:
             s = s + bias
         if mask is not None:
@@ -120,6 +126,8 @@ def attn_block_bwd_ref(
     dropout_mask: Optional[torch.Tensor] = None,
     delta: Optional[torch.Tensor] = None,
     q_chunk: int = 2048,
+    q_grp: Optional[torch.Tensor] = None,
+    k_grp: Optional[torch.Tensor] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Block backward given the FINAL (merged) ``out``/``lse`` of the rows -> fp32 (dq, dk, dv).
 
@@ -147,7 +155,8 @@ def attn_block_bwd_ref(
             s = softcap * t
         else:
             s = raw
-        mask, bias = _bias_and_mask(q_pos[s0:s1], k_pos, causal, window_size, alibi_slopes, H, dev)
+        mask, bias = _bias_and_mask(q_pos[s0:s1], k_pos, causal, window_size, alibi_slopes, H, dev,
+                                    None if q_grp is None else q_grp[s0:s1], k_grp)
         if bias is not None:
             s = s + bias
         if mask is not None:

@@ -33,6 +33,7 @@ class Seg:
     start: int
     count: int
     stride: int = 1
+    group: int = 0      # tokens only attend within their group (varlen: one group per sequence)
 
     @property
     def last(self) -> int:
@@ -78,6 +79,30 @@ def pos_tensor(spec: PosSpec, device=None) -> torch.Tensor:
     return torch.cat(parts) if len(parts) > 1 else parts[0]
 
 
+def group_tensor(spec: PosSpec, device=None) -> torch.Tensor:
+    return torch.cat([torch.full((s.count,), s.group, dtype=torch.int64, device=device) for s in spec])
+
+
+def has_groups(spec: PosSpec) -> bool:
+    return any(s.group != 0 for s in spec)
+
+
+def varlen_positions(variant: str, ring_rank: int, ring_degree: int, cu_seqlens) -> PosSpec:
+    """Positions of a packed (varlen) local shard: sequence ``i`` contributes
+    ``cu_seqlens[i+1]-cu_seqlens[i]`` local tokens laid out like a dense shard of that length and
+    forms attention group ``i``.  (Reference: per-sequence halves in
+    ``zigzag_ring_flash_attn_varlen.py:27-42``.)"""
+    cu = [int(x) for x in cu_seqlens]
+    out = []
+    for i in range(len(cu) - 1):
+        L = cu[i + 1] - cu[i]
+        if L == 0:
+            continue
+        for s in ring_positions(variant, ring_rank, ring_degree, L):
+            out.append(Seg(s.start, s.count, s.stride, i))
+    return tuple(out)
+
+
 def pos_min_max(spec: PosSpec) -> Tuple[int, int]:
     lo = min(min(s.start, s.last) for s in spec if s.count > 0)
     hi = max(max(s.start, s.last) for s in spec if s.count > 0)
@@ -95,7 +120,7 @@ def slice_pos(spec: PosSpec, begin: int, end: int) -> PosSpec:
     for s in spec:
         lo, hi = max(begin, off), min(end, off + s.count)
         if hi > lo:
-            out.append(Seg(s.start + (lo - off) * s.stride, hi - lo, s.stride))
+            out.append(Seg(s.start + (lo - off) * s.stride, hi - lo, s.stride, s.group))
         off += s.count
     return tuple(out)
 

@@ -1,0 +1,198 @@
+"""Ring attention over a process group -- collective (NCCL/gloo P2P) path, all variants.
+
+Parity: ``yunchang/ring/ring_flash_attn.py`` (basic), ``zigzag_ring_flash_attn.py``,
+``stripe_flash_attn.py`` -- forward loops, backward loops with the travelling fp32 dK/dV ring,
+and the ``autograd.Function`` wrappers (``ring_flash_attn.py:7-224`` etc.).
+
+Design difference: the three reference files hard-code their masking cases per ring step
+(``step <= rank`` / half-slicing / shifted slicing).  Here ONE loop serves every variant because
+each block is described by the *global positions* of its tokens
+(:func:`lca_b200.parallel.layout.ring_positions`) and the attention op masks on positions.
+Consequences: sliding windows and ALiBi are exact across blocks (the reference is only right
+for ``window=(-1,-1)`` and asserts ``alibi_slopes is None``), non-causal zigzag/stripe work, and
+fully-masked blocks are skipped by a position-range test instead of variant-specific rules.
+The zigzag/stripe load balance is preserved because the kernel skips fully masked tiles.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ..globals import group_rank, group_size
+from ..ops import native
+from ..ops.attention import (AttnParams, attn_block_bwd, attn_block_fwd, block_is_visible,
+                             merge_out_lse_)
+from .layout import canonical_variant, ring_positions, varlen_positions
+from .ring_comm import RingComm
+
+
+def _engine_for(attn_type) -> Optional[str]:
+    """AttnType -> engine name (None = auto: native on Blackwell, torch elsewhere)."""
+    if attn_type is None:
+        return None
+    name = getattr(attn_type, "value", attn_type)
+    if isinstance(name, str) and name.startswith("torch"):
+        return "torch"
+    return None
+
+
+def _dropout_mask(seed: int, rank: int, src: int, B, H, Sq, Sk, p_drop, device):
+    if p_drop <= 0.0:
+        return None
+    g = torch.Generator(device=device)
+    g.manual_seed((seed * 1000003 + rank * 8191 + src) & 0x7FFFFFFFFFFF)
+    return torch.rand((B, H, Sq, Sk), generator=g, device=device) >= p_drop
+
+
+def _pos_builders(variant, R, Lq, Lk, cu_seqlens_q=None, cu_seqlens_k=None):
+    """-> (qpos(rank), kpos(rank)) closures; dense shards or packed varlen shards."""
+    if cu_seqlens_q is None:
+        return (lambda rr: ring_positions(variant, rr, R, Lq)), (lambda rr: ring_positions(variant, rr, R, Lk))
+    cq = [int(x) for x in cu_seqlens_q]
+    ck = cq if cu_seqlens_k is None else [int(x) for x in cu_seqlens_k]
+    return (lambda rr: varlen_positions(variant, rr, R, cq)), (lambda rr: varlen_positions(variant, rr, R, ck))
+
+
+def ring_attn_forward(group, q, k, v, variant: str, p: AttnParams, engine=None, dropout_seed: int = 0,
+                      cu_seqlens_q=None, cu_seqlens_k=None):
+    """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32.  With ``cu_seqlens`` the tensors are packed
+    ``(1, total, H, D)`` shards and every sequence is its own attention group."""
+    R, r = group_size(group), group_rank(group)
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    qpos_of, kpos_of = _pos_builders(variant, R, Lq, Lk, cu_seqlens_q, cu_seqlens_k)
+    q_pos = qpos_of(r)
+    if R == 1:
+        dm = _dropout_mask(dropout_seed, r, r, B, H, Lq, Lk, p.dropout_p, q.device)
+        return attn_block_fwd(q, k, v, q_pos, kpos_of(0), p, engine, dm)
+    comm = RingComm(group)
+    k, v = k.contiguous(), v.contiguous()      # P2P payloads must be dense (packed-QKV views are not)
+    out_acc = lse_acc = None
+    next_k = next_v = None
+    for step in range(R):
+        if step + 1 != R:
+            next_k, next_v = comm.send_recv(k), comm.send_recv(v)
+            comm.commit()
+        src = (r - step) % R
+        k_pos = kpos_of(src)
+        if block_is_visible(q_pos, k_pos, p):
+            dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
+            bo, bl = attn_block_fwd(q, k, v, q_pos, k_pos, p, engine, dm)
+            if out_acc is None:
+                out_acc, lse_acc = bo.to(torch.float32), bl
+            else:
+                merge_out_lse_(out_acc, lse_acc, bo, bl)
+        if step + 1 != R:
+            comm.wait()
+            k, v = next_k, next_v
+    if out_acc is None:  # nothing visible at all (e.g. window excludes every block)
+        return (torch.zeros_like(q), torch.full((B, H, Lq), float("-inf"), dtype=torch.float32, device=q.device))
+    out = native.finalize_out(out_acc, q.dtype) if out_acc.is_cuda else out_acc.to(q.dtype)
+    return out, lse_acc
+
+
+def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnParams, engine=None,
+                       dropout_seed: int = 0, cu_seqlens_q=None, cu_seqlens_k=None):
+    """-> (dq, dk, dv) in the input dtypes.  dK/dV partial sums travel with their K/V block in fp32
+    and arrive at the owner after R hops (same scheme as ``ring_flash_attn.py:65-147``)."""
+    R, r = group_size(group), group_rank(group)
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    qpos_of, kpos_of = _pos_builders(variant, R, Lq, Lk, cu_seqlens_q, cu_seqlens_k)
+    q_pos = qpos_of(r)
+    if q.is_cuda and native.available() and dout.dtype in (torch.bfloat16, torch.float16):
+        delta = native.ext().attn_delta(out, dout.contiguous() if dout.stride(-1) != 1 else dout)
+    else:
+        delta = (dout.to(torch.float32) * out.to(torch.float32)).sum(-1).permute(0, 2, 1).contiguous()
+    if R == 1:
+        dm = _dropout_mask(dropout_seed, r, r, B, H, Lq, Lk, p.dropout_p, q.device)
+        dq, dk, dv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, kpos_of(0), p, engine, dm, delta)
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
+    kv_comm, dkv_comm = RingComm(group), RingComm(group)
+    k, v = k.contiguous(), v.contiguous()
+    dq = None
+    dk_acc = dv_acc = next_dk = next_dv = next_k = next_v = None
+    for step in range(R):
+        if step + 1 != R:
+            next_k, next_v = kv_comm.send_recv(k), kv_comm.send_recv(v)
+            kv_comm.commit()
+        src = (r - step) % R
+        k_pos = kpos_of(src)
+        bdk = bdv = None
+        if block_is_visible(q_pos, k_pos, p):
+            dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
+            bdq, bdk, bdv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta)
+            dq = bdq.to(torch.float32) if dq is None else dq.add_(bdq)
+            bdk, bdv = bdk.to(torch.float32), bdv.to(torch.float32)
+        if step == 0:
+            dk_acc = bdk if bdk is not None else torch.zeros(k.shape, dtype=torch.float32, device=k.device)
+            dv_acc = bdv if bdv is not None else torch.zeros(v.shape, dtype=torch.float32, device=v.device)
+        else:
+            dkv_comm.wait()
+            dk_acc = next_dk if bdk is None else next_dk.add_(bdk)
+            dv_acc = next_dv if bdv is None else next_dv.add_(bdv)
+        if step + 1 != R:
+            kv_comm.wait()
+            k, v = next_k, next_v
+        next_dk, next_dv = dkv_comm.send_recv(dk_acc), dkv_comm.send_recv(dv_acc)
+        dkv_comm.commit()
+    dkv_comm.wait()
+    if dq is None:
+        dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    return dq.to(q.dtype), next_dk.to(k.dtype), next_dv.to(v.dtype)
+
+
+class RingAttnFunc(torch.autograd.Function):
+    """One autograd node for every ring variant (reference: RingFlashAttnFunc /
+    ZigZagRingFlashAttnFunc / StripeFlashAttnFunc)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, variant, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
+                deterministic, return_softmax, group, attn_type, attn_processor):
+        p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
+        engine = _engine_for(attn_type)
+        seed = int(torch.randint(0, 2**31 - 1, (1,)).item()) if p.dropout_p > 0 else 0
+        out, lse = ring_attn_forward(group, q, k, v, variant, p, engine, seed)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.p, ctx.variant, ctx.group, ctx.engine, ctx.seed = p, variant, group, engine, seed
+        if return_softmax:
+            ctx.mark_non_differentiable(lse)
+            return out, lse, None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        q, k, v, out, lse = ctx.saved_tensors
+        dq, dk, dv = ring_attn_backward(ctx.group, dout, q, k, v, out, lse, ctx.variant, ctx.p, ctx.engine, ctx.seed)
+        return (dq, dk, dv) + (None,) * 12
+
+
+def _make_funcs(variant: str):
+    variant = canonical_variant(variant)
+
+    def func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+             alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
+             attn_processor=None):
+        return RingAttnFunc.apply(q, k, v, variant, dropout_p, softmax_scale, causal, window_size, softcap,
+                                  alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+
+    def kvpacked(q, kv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                 alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
+                 attn_processor=None):
+        return func(q, kv[:, :, 0], kv[:, :, 1], dropout_p, softmax_scale, causal, window_size, softcap,
+                    alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+
+    def qkvpacked(qkv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                  alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
+                  attn_processor=None):
+        return func(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dropout_p, softmax_scale, causal, window_size,
+                    softcap, alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+
+    return func, kvpacked, qkvpacked
+
+
+ring_flash_attn_func, ring_flash_attn_kvpacked_func, ring_flash_attn_qkvpacked_func = _make_funcs("basic")
+(zigzag_ring_flash_attn_func, zigzag_ring_flash_attn_kvpacked_func,
+ zigzag_ring_flash_attn_qkvpacked_func) = _make_funcs("zigzag")
+stripe_flash_attn_func, stripe_flash_attn_kvpacked_func, stripe_flash_attn_qkvpacked_func = _make_funcs("stripe")

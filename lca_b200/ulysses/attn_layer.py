@@ -1,0 +1,69 @@
+"""``UlyssesAttention`` -- pure DeepSpeed-Ulysses sequence parallelism (all-to-all only, no ring).
+
+Parity: ``yunchang/ulysses/attn_layer.py:15-125``: ``3 x a2a -> local attention -> a2a`` with an
+explicit ``sequence_process_group``.  The local attention is the position-aware block op, so
+causal / window / softcap / ALiBi (sliced per head shard -- the reference passes the un-sharded
+slopes, ``:110``) / GQA all work, forward and backward.  On NVLink groups the fused engine is used
+(one kernel: push + tcgen05 attention + O scatter).
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+from torch import Tensor
+
+from ..globals import PROCESS_GROUP, group_size
+from ..kernels import AttnType, select_flash_attn_impl
+from ..parallel.all_to_all import SeqAllToAll4D
+from ..hybrid.attn_layer import _resolve_backend, _slice_alibi
+
+
+class UlyssesAttention(torch.nn.Module):
+    def __init__(self, sequence_process_group=None, scatter_idx: int = 2, gather_idx: int = 1,
+                 use_sync: bool = False, attn_type: AttnType = AttnType.FA, backend: Optional[str] = None) -> None:
+        super().__init__()
+        self.spg = sequence_process_group
+        self.scatter_idx, self.gather_idx = scatter_idx, gather_idx
+        self.use_sync = use_sync
+        self.attn_type = attn_type
+        self.attn_fn = select_flash_attn_impl(attn_type, stage="fwd-bwd")
+        self.backend = _resolve_backend(backend)
+        self._fused = None
+
+    def _fused_engine(self, q: Tensor):
+        if self.backend == "collective":
+            return None
+        from ..parallel import fused
+
+        if self._fused is None:
+            self._fused = fused.get_ulysses_engine_if_supported(self.spg, q, strict=self.backend == "fused") or False
+        return self._fused or None
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, dropout_p=0.0, softmax_scale=None, causal=False,
+                window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False,
+                *args: Any) -> Tensor:
+        eng = None
+        if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
+            eng = self._fused_engine(query)
+        if eng is not None:
+            return eng.attention(query, key, value, "basic", softmax_scale, causal, window_size, softcap,
+                                 alibi_slopes, deterministic)
+        q = SeqAllToAll4D.apply(self.spg, query, self.scatter_idx, self.gather_idx, self.use_sync)
+        k = SeqAllToAll4D.apply(self.spg, key, self.scatter_idx, self.gather_idx, self.use_sync)
+        v = SeqAllToAll4D.apply(self.spg, value, self.scatter_idx, self.gather_idx, self.use_sync)
+        if softmax_scale is None:
+            softmax_scale = q.shape[-1] ** -0.5
+        if dropout_p and dropout_p > 0:
+            from ..parallel.ring_attention import ring_flash_attn_func
+            ctx = ring_flash_attn_func(q, k, v, dropout_p, softmax_scale, causal, window_size, softcap,
+                                       _slice_alibi(alibi_slopes, self.spg), deterministic, False, None,
+                                       self.attn_type)
+        else:
+            ctx = self.attn_fn(q, k, v, dropout_p=0.0, softmax_scale=softmax_scale, causal=causal,
+                               window_size=window_size, softcap=softcap,
+                               alibi_slopes=_slice_alibi(alibi_slopes, self.spg), deterministic=deterministic,
+                               return_attn_probs=return_attn_probs)
+        if isinstance(ctx, tuple):
+            ctx = ctx[0]
+        return SeqAllToAll4D.apply(self.spg, ctx, self.gather_idx, self.scatter_idx, self.use_sync)

@@ -1,0 +1,195 @@
+"""gloo multi-process tests of every distributed code path (BASELINE config 1 lives here).
+Pattern follows the reference's tests (test/test_hybrid_attn.py: broadcast global tensors, shard with
+EXTRACT_FUNC_DICT, run the module, compare against the single-device result sharded the same way) but
+with hard forward AND backward assertions."""
+import pytest
+import torch
+import torch.distributed as dist
+
+from dist_utils import run_distributed
+
+
+def _global_inputs(B, S, H, Hkv, D, seed=0, packed=False):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, S, H, D, generator=g)
+    k = torch.randn(B, S, Hkv, D, generator=g)
+    v = torch.randn(B, S, Hkv, D, generator=g)
+    do = torch.randn(B, S, H, D, generator=g)
+    return q, k, v, do
+
+
+def _reference(q, k, v, do, **kw):
+    from lca_b200.ops.ref_attention import attention_ref
+    from lca_b200.kernels.attention import pytorch_attn_func
+    q, k, v = (t.clone().requires_grad_() for t in (q, k, v))
+    out = pytorch_attn_func(q, k, v, **kw)
+    out.backward(do)
+    return out.detach(), q.grad, k.grad, v.grad
+
+
+# ------------------------------------------------------------------------------------------ a2a
+def _a2a_worker(rank, world):
+    from lca_b200.parallel.all_to_all import SeqAllToAll4D, SeqAllToAll5D
+    B, Sl, H, D = 2, 3, 2 * world, 4
+    full = torch.arange(B * Sl * world * H * D, dtype=torch.float32).view(B, Sl * world, H, D)
+    x = full[:, rank * Sl:(rank + 1) * Sl].clone().requires_grad_()
+    y = SeqAllToAll4D.apply(None, x, 2, 1)
+    hl = H // world
+    assert torch.equal(y, full[:, :, rank * hl:(rank + 1) * hl])            # token order + head ownership
+    z = SeqAllToAll4D.apply(None, y, 1, 2)
+    assert torch.equal(z, x)
+    z.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    full5 = torch.arange(B * Sl * world * 3 * H * D, dtype=torch.float32).view(B, Sl * world, 3, H, D)
+    x5 = full5[:, rank * Sl:(rank + 1) * Sl].clone()
+    y5 = SeqAllToAll5D.apply(None, x5, 3, 1)
+    assert torch.equal(y5, full5[:, :, :, rank * hl:(rank + 1) * hl])
+    assert torch.equal(SeqAllToAll5D.apply(None, y5, 1, 3), x5)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_all_to_all(world):
+    run_distributed(_a2a_worker, world)
+
+
+# ------------------------------------------------------------------------------------------ hybrid
+def _hybrid_worker(rank, world, U, R, variant, kw, module, H, Hkv):
+    import lca_b200
+    from lca_b200 import (AsyncLongContextAttention, EXTRACT_FUNC_DICT, LongContextAttention,
+                          LongContextAttentionQKVPacked, UlyssesAttention, set_seq_parallel_pg)
+    from lca_b200.kernels import AttnType
+    B, S, D = 1, 16 * world, 8
+    q, k, v, do = _global_inputs(B, S, H, Hkv, D, seed=1)
+    ro, rdq, rdk, rdv = _reference(q, k, v, do, **kw)
+    set_seq_parallel_pg(U, R, rank, world)
+    ex = EXTRACT_FUNC_DICT[variant]
+    sh = lambda t: ex(t, rank, world, rd=R, ud=U).detach().clone()
+    lq, lk, lv, ldo = sh(q), sh(k), sh(v), sh(do)
+    for t in (lq, lk, lv):
+        t.requires_grad_()
+    if module == "hybrid":
+        out = LongContextAttention(ring_impl_type=variant, attn_type=AttnType.TORCH)(lq, lk, lv, **kw)
+    elif module == "hybrid_pack":
+        out = LongContextAttention(ring_impl_type=variant, attn_type=AttnType.TORCH, use_pack_qkv=True)(lq, lk, lv, **kw)
+    elif module == "async":
+        out = AsyncLongContextAttention(ring_impl_type=variant, attn_type=AttnType.TORCH)(lq, lk, lv, **kw)
+    elif module == "ulysses":
+        out = UlyssesAttention(None, attn_type=AttnType.TORCH)(lq, lk, lv, **kw)
+    elif module == "qkvpacked":
+        qkv = torch.stack([lq, lk, lv], dim=2)
+        out = LongContextAttentionQKVPacked(ring_impl_type=variant, attn_type=AttnType.TORCH)(qkv, **kw)
+    out.backward(ldo)
+    torch.testing.assert_close(out, sh(ro), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lq.grad, sh(rdq), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lk.grad, sh(rdk), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lv.grad, sh(rdv), atol=2e-5, rtol=1e-4)
+
+
+CAUSAL = dict(causal=True)
+
+
+@pytest.mark.parametrize("U,R,variant,kw,module,H,Hkv", [
+    (1, 2, "basic", CAUSAL, "hybrid", 8, 8),                 # BASELINE config 1 shape class (ring=2, ulysses=1)
+    (1, 4, "zigzag", CAUSAL, "hybrid", 4, 4),
+    (1, 4, "strip", CAUSAL, "hybrid", 4, 2),
+    (2, 2, "zigzag", CAUSAL, "hybrid", 4, 2),                # GQA through Ulysses + ring
+    (2, 2, "strip", dict(causal=True, window_size=(11, 0)), "hybrid", 4, 4),   # exact window across blocks
+    (2, 2, "basic", dict(causal=False, window_size=(5, 9)), "hybrid", 4, 4),
+    (4, 1, "basic", dict(causal=True, softcap=5.0), "hybrid", 4, 4),
+    (2, 2, "zigzag", CAUSAL, "hybrid_pack", 4, 4),
+    (2, 2, "zigzag", CAUSAL, "qkvpacked", 4, 4),
+    (2, 2, "basic", dict(causal=False), "qkvpacked", 4, 4),
+    (2, 2, "zigzag", CAUSAL, "async", 4, 2),
+    (4, 1, "basic", CAUSAL, "ulysses", 8, 4),
+])
+def test_usp_modules_match_single_device(U, R, variant, kw, module, H, Hkv):
+    run_distributed(_hybrid_worker, U * R, U, R, variant, kw, module, H, Hkv)
+
+
+def _baseline_config1_worker(rank, world):
+    """BASELINE.json config 1: LongContextAttention basic, TORCH attn, ulysses=1 ring=2, gloo, S=1024 h=8 d=64."""
+    from lca_b200 import EXTRACT_FUNC_DICT, LongContextAttention, set_seq_parallel_pg
+    from lca_b200.kernels import AttnType
+    q, k, v, do = _global_inputs(1, 1024, 8, 8, 64, seed=3)
+    ro, rdq, rdk, rdv = _reference(q, k, v, do, causal=True)
+    set_seq_parallel_pg(1, 2, rank, world)
+    sh = lambda t: EXTRACT_FUNC_DICT["basic"](t, rank, world, rd=2, ud=1).detach().clone()
+    lq, lk, lv = (sh(t).requires_grad_() for t in (q, k, v))
+    out = LongContextAttention(ring_impl_type="basic", attn_type=AttnType.TORCH)(lq, lk, lv, causal=True)
+    out.backward(sh(do))
+    torch.testing.assert_close(out, sh(ro), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lq.grad, sh(rdq), atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(lk.grad, sh(rdk), atol=5e-5, rtol=1e-4)
+
+
+def test_baseline_config1_cpu_gloo():
+    run_distributed(_baseline_config1_worker, 2)
+
+
+def _alibi_worker(rank, world):
+    from lca_b200 import EXTRACT_FUNC_DICT, LongContextAttention, set_seq_parallel_pg
+    from lca_b200.kernels import AttnType
+    U, R = 2, 2
+    q, k, v, do = _global_inputs(1, 64, 4, 4, 8, seed=5)
+    slopes = torch.tensor([0.5, 0.25, 0.125, 0.0625])
+    ro, rdq, _, _ = _reference(q, k, v, do, causal=True, alibi_slopes=slopes)
+    set_seq_parallel_pg(U, R, rank, world)
+    sh = lambda t: EXTRACT_FUNC_DICT["zigzag"](t, rank, world, rd=R, ud=U).detach().clone()
+    lq, lk, lv = (sh(t).requires_grad_() for t in (q, k, v))
+    out = LongContextAttention(ring_impl_type="zigzag", attn_type=AttnType.TORCH)(lq, lk, lv, causal=True, alibi_slopes=slopes)
+    out.backward(sh(do))
+    torch.testing.assert_close(out, sh(ro), atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(lq.grad, sh(rdq), atol=2e-5, rtol=1e-4)
+
+
+def test_alibi_through_usp():
+    run_distributed(_alibi_worker, 4)
+
+
+def _varlen_worker(rank, world, variant):
+    from lca_b200 import ring_flash_attn_varlen_func, zigzag_ring_flash_attn_varlen_func
+    from lca_b200.kernels import AttnType
+    from lca_b200.kernels.attention import pytorch_attn_func
+    from lca_b200.parallel.layout import local_token_index
+    R, H, D = world, 2, 8
+    glens = [8 * R, 4 * R, 12 * R]
+    g = torch.Generator().manual_seed(7)
+    seqs = [tuple(torch.randn(1, L, H, D, generator=g) for _ in range(4)) for L in glens]
+    fn = ring_flash_attn_varlen_func if variant == "basic" else zigzag_ring_flash_attn_varlen_func
+    loc, refs = [], []
+    for (q, k, v, do) in seqs:
+        q1, k1, v1 = (t.clone().requires_grad_() for t in (q, k, v))
+        o = pytorch_attn_func(q1, k1, v1, causal=True)
+        o.backward(do)
+        idx = local_token_index(variant, q.shape[1], 0, rank, 1, R)
+        loc.append(tuple(t[0, idx] for t in (q, k, v, do)))
+        refs.append(tuple(t[0, idx] for t in (o.detach(), q1.grad, k1.grad, v1.grad)))
+    lq, lk, lv, ldo = (torch.cat([l[i] for l in loc]).requires_grad_() for i in range(4))
+    cu = torch.tensor([0] + list(torch.tensor([l[0].shape[0] for l in loc]).cumsum(0)), dtype=torch.int32)
+    out = fn(lq, lk, lv, cu, max(l[0].shape[0] for l in loc), causal=True, attn_type=AttnType.TORCH)
+    out.backward(ldo.detach())
+    for i, name in enumerate(["out", "dq", "dk", "dv"]):
+        got = [out, lq.grad, lk.grad, lv.grad][i]
+        torch.testing.assert_close(got, torch.cat([r[i] for r in refs]), atol=2e-5, rtol=1e-4, msg=name)
+
+
+@pytest.mark.parametrize("variant", ["basic", "zigzag"])
+def test_varlen_ring(variant):
+    run_distributed(_varlen_worker, 2, variant)
+
+
+def _dp_worker(rank, world):
+    """dp_degree > 1: two replicas of a 1x2 mesh shard identically (reference never tests this)."""
+    from lca_b200 import EXTRACT_FUNC_DICT, LongContextAttention, PROCESS_GROUP, set_seq_parallel_pg
+    from lca_b200.kernels import AttnType
+    set_seq_parallel_pg(1, 2, rank, world)
+    assert PROCESS_GROUP.mesh.dp_degree == 2
+    q, k, v, do = _global_inputs(1, 32, 2, 2, 8, seed=9)
+    ro, *_ = _reference(q, k, v, do, causal=True)
+    sh = lambda t: EXTRACT_FUNC_DICT["strip"](t, rank, world, rd=2, ud=1)
+    out = LongContextAttention(ring_impl_type="strip", attn_type=AttnType.TORCH)(sh(q), sh(k), sh(v), causal=True)
+    torch.testing.assert_close(out, sh(ro), atol=2e-5, rtol=1e-4)
+
+
+def test_dp_replicas():
+    run_distributed(_dp_worker, 4)

@@ -1,0 +1,114 @@
+"""CPU tests of the oracle itself: vs torch SDPA, autograd-consistency of the explicit backward,
+merge exactness, block decomposition == whole."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lca_b200.ops.attention import AttnParams, attn_block_bwd, attn_block_fwd, merge_out_lse_
+from lca_b200.ops.ref_attention import attention_ref, attn_block_bwd_ref, attn_block_fwd_ref
+from lca_b200.parallel.layout import Seg, pos_tensor, ring_positions
+
+
+def _qkv(B, Sq, Sk, H, Hkv, D, dtype=torch.float32, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, Sq, H, D, generator=g, dtype=dtype), torch.randn(B, Sk, Hkv, D, generator=g, dtype=dtype),
+            torch.randn(B, Sk, Hkv, D, generator=g, dtype=dtype))
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("H,Hkv", [(4, 4), (4, 2), (4, 1)])
+def test_matches_sdpa(causal, H, Hkv):
+    q, k, v = _qkv(2, 33, 33, H, Hkv, 16)
+    out, lse = attention_ref(q, k, v, causal=causal)
+    kk, vv = (t.repeat_interleave(H // Hkv, dim=2) for t in (k, v))
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), is_causal=causal)
+    torch.testing.assert_close(out, ref.transpose(1, 2), atol=1e-5, rtol=1e-5)
+    s = torch.einsum("bqhd,bkhd->bhqk", q, kk) / math.sqrt(16)
+    if causal:
+        s = s.masked_fill(torch.ones(33, 33, dtype=torch.bool).triu(1), float("-inf"))
+    torch.testing.assert_close(lse, torch.logsumexp(s, -1), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kw", [dict(causal=True), dict(window_size=(5, 3)), dict(causal=True, window_size=(7, -1)),
+                                dict(softcap=3.0), dict(alibi=True, causal=True), dict()])
+def test_explicit_backward_matches_autograd(kw):
+    kw = dict(kw)
+    q, k, v = _qkv(2, 24, 24, 4, 2, 8, torch.float64)
+    alibi = torch.rand(4, dtype=torch.float64) if kw.pop("alibi", False) else None
+    qp = kp = torch.arange(24)
+    scale = 0.3
+    q1, k1, v1 = (t.clone().requires_grad_() for t in (q, k, v))
+    causal = kw.get("causal", False)
+    ws = kw.get("window_size", (-1, -1))
+    sc = kw.get("softcap", 0.0)
+    # differentiable re-implementation through plain autograd
+    kk, vv = (t.repeat_interleave(2, dim=2) for t in (k1, v1))
+    s = torch.einsum("bqhd,bkhd->bhqk", q1, kk) * scale
+    if sc > 0:
+        s = sc * torch.tanh(s / sc)
+    rel = kp.view(1, -1) - qp.view(-1, 1)
+    if alibi is not None:
+        s = s - alibi.view(1, -1, 1, 1) * rel.abs()
+    m = torch.zeros(24, 24, dtype=torch.bool)
+    if causal:
+        m |= rel > 0
+    if ws[0] >= 0:
+        m |= rel < -ws[0]
+    if ws[1] >= 0 and not causal:
+        m |= rel > ws[1]
+    s = s.masked_fill(m, float("-inf"))
+    o_auto = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), vv)
+    do = torch.randn_like(o_auto)
+    o_auto.backward(do)
+    out, lse = attn_block_fwd_ref(q.float(), k.float(), v.float(), qp, kp, scale, causal, ws, sc,
+                                  None if alibi is None else alibi.float())
+    torch.testing.assert_close(out.double(), o_auto.detach(), atol=1e-4, rtol=1e-4)
+    dq, dk, dv = attn_block_bwd_ref(do.float(), q.float(), k.float(), v.float(), out, lse, qp, kp, scale, causal, ws, sc,
+                                    None if alibi is None else alibi.float())
+    torch.testing.assert_close(dq.double(), q1.grad, atol=1e-4, rtol=1e-3)
+    torch.testing.assert_close(dk.double(), k1.grad, atol=1e-4, rtol=1e-3)
+    torch.testing.assert_close(dv.double(), v1.grad, atol=1e-4, rtol=1e-3)
+
+
+@pytest.mark.parametrize("variant", ["basic", "zigzag", "stripe"])
+@pytest.mark.parametrize("kw", [dict(causal=True), dict(causal=True, window_size=(9, 0)), dict(causal=False)])
+def test_block_decomposition_equals_whole(variant, kw):
+    """Shard -> per-block attention with global positions -> merge == unsharded attention.  This is the
+    single-process model of the ring and covers empty rows (-inf LSE) in the merge."""
+    R, S, H, D = 4, 64, 2, 8
+    q, k, v = _qkv(1, S, S, H, H, D)
+    p = AttnParams.make(q, None, kw.get("causal", False), kw.get("window_size", (-1, -1)))
+    ref_o, ref_l = attention_ref(q, k, v, **kw)
+    for r in range(R):
+        qpos = ring_positions(variant, r, R, S // R)
+        qi = q[:, pos_tensor(qpos)]
+        acc_o = torch.zeros(1, S // R, H, D)
+        acc_l = torch.full((1, H, S // R), float("-inf"))
+        for src in range(R):
+            kpos = ring_positions(variant, src, R, S // R)
+            idx = pos_tensor(kpos)
+            bo, bl = attn_block_fwd(qi, k[:, idx], v[:, idx], qpos, kpos, p, "torch")
+            merge_out_lse_(acc_o, acc_l, bo, bl)
+        torch.testing.assert_close(acc_o, ref_o[:, pos_tensor(qpos)], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(acc_l, ref_l[:, :, pos_tensor(qpos)], atol=1e-5, rtol=1e-5)
+
+
+def test_fully_masked_rows_are_zero_and_minus_inf():
+    q, k, v = _qkv(1, 4, 4, 1, 1, 8)
+    out, lse = attn_block_fwd_ref(q, k, v, torch.arange(4), torch.arange(4) + 10, 1.0, causal=True)
+    assert torch.all(out == 0) and torch.all(torch.isinf(lse) & (lse < 0))
+    acc_o, acc_l = torch.zeros(1, 4, 1, 8), torch.full((1, 1, 4), float("-inf"))
+    merge_out_lse_(acc_o, acc_l, out, lse)
+    assert not torch.isnan(acc_o).any() and torch.all(torch.isinf(acc_l))
+
+
+def test_groups_block_diagonal():
+    q, k, v = _qkv(1, 10, 10, 2, 2, 8)
+    spec = (Seg(0, 4, 1, 0), Seg(0, 6, 1, 1))
+    p = AttnParams.make(q, None, True)
+    out, lse = attn_block_fwd(q, k, v, spec, spec, p, "torch")
+    o0, _ = attention_ref(q[:, :4], k[:, :4], v[:, :4], causal=True)
+    o1, _ = attention_ref(q[:, 4:], k[:, 4:], v[:, 4:], causal=True)
+    torch.testing.assert_close(out, torch.cat([o0, o1], 1), atol=1e-5, rtol=1e-5)
