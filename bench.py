@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Headline benchmark: sequence-parallel causal attention throughput (aggregate TFLOPS over N GPUs).
+
+Contract (see task brief): ``python bench.py --gpus N --steps K --warmup W [--impl reference]`` prints
+ONE JSON line on rank 0.  For N > 1 it is launched under torchrun (RANK/LOCAL_RANK/WORLD_SIZE env).
+
+Config = BASELINE.json config 3 ("pure ring path") generalised over N:
+  LongContextAttention(ring_impl_type="zigzag"), ulysses=1, ring=N, global seq 256K, h=8, d=128, bf16,
+  causal, B=1, strong scaling (global problem fixed, each rank owns S/N tokens).
+Both arms (ours / the unmodified reference from baseline/_ref with flash-attn 2.8.3 + NCCL) run the
+same module API, the same shapes, the same timing harness.
+
+value        device-timed (CUDA events, max over ranks) attention TFLOPS with inputs resident on device
+e2e.value    same metric through the public API including, every step, the H2D copy of that step's
+             q/k/v shards from pinned host memory and a D2H read of a scalar result
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("LCA_BENCH_MODE", "fwd"), choices=["fwd", "fwdbwd"])
+    ap.add_argument("--seq", type=int, default=256 * 1024, help="GLOBAL sequence length")
+    ap.add_argument("--heads", type=int, default=8)
+    ap.add_argument("--kv-heads", type=int, default=0)
+    ap.add_argument("--head-dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--ulysses", type=int, default=1)
+    ap.add_argument("--ring-impl", default="zigzag", choices=["basic", "zigzag", "strip"])
+    ap.add_argument("--no-causal", action="store_true")
+    ap.add_argument("--backend", default=None, help="ours: auto|fused|collective")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons of this rank's GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.15)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        clocks = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max((int(s[1]) for s in self.samples if s[1].isdigit()), default=0)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": mx or None,
+                "reasons": reasons, "samples": len(clocks)}
+
+
+def main():
+    a = parse()
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    if a.impl == "reference":
+        ref_dir = os.path.join(ROOT, "baseline", "_ref")
+        if not os.path.isdir(os.path.join(ref_dir, "yunchang")):
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/yunchang missing (pip install --target failed)"}))
+            return
+        sys.path.insert(0, ref_dir)
+    need_dist = world > 1 or a.impl == "reference"
+    if need_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    N = world
+    U = min(a.ulysses, N)
+    R = N // U
+    B, S, H, D = a.batch, a.seq, a.heads, a.head_dim
+    Hkv = a.kv_heads or H
+    causal = not a.no_causal
+    Sl = S // N
+    assert S % (2 * N) == 0
+    dtype = torch.bfloat16
+
+    if a.impl == "reference":
+        try:
+            import yunchang
+            from yunchang import LongContextAttention, set_seq_parallel_pg
+            from yunchang.kernels import AttnType
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": f"import yunchang failed: {type(e).__name__}: {str(e)[:120]}"}))
+            return
+        set_seq_parallel_pg(U, R, rank, world)
+        attn = LongContextAttention(ring_impl_type=a.ring_impl, attn_type=AttnType.FA)
+        launches = lambda: 0
+        native_ok = None
+    else:
+        import lca_b200
+        from lca_b200 import LongContextAttention, set_seq_parallel_pg
+        from lca_b200.ops import native
+
+        set_seq_parallel_pg(U, R, rank, world)
+        attn = LongContextAttention(ring_impl_type=a.ring_impl, backend=a.backend)
+        launches = lambda: native.LAUNCHES
+        native_ok = native.available()
+        assert native_ok, "native sm_100a extension not available on this GPU box"
+
+    # synthetic shards, generated on host in pinned memory (this rank's S/N tokens)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.randn(B, Sl, h, D, generator=g, dtype=torch.float32).to(dtype).pin_memory() for h in (H, Hkv, Hkv)]
+    host_do = torch.randn(B, Sl, H, D, generator=g, dtype=torch.float32).to(dtype).pin_memory()
+    need_grad = a.mode == "fwdbwd"
+
+    def to_dev(non_blocking=True):
+        ts = [t.to(dev, non_blocking=non_blocking) for t in host]
+        if need_grad:
+            ts = [t.requires_grad_() for t in ts]
+        return ts
+
+    dout = host_do.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(q, k, v):
+        if need_grad:
+            out = attn(q, k, v, causal=causal)
+            out.backward(dout)
+            return out
+        with torch.no_grad():
+            return attn(q, k, v, causal=causal)
+
+    def barrier():
+        if need_dist and world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident timing
+    q, k, v = to_dev(False)
+    for _ in range(max(a.warmup, 3)):
+        step(q, k, v)
+        flush.fill_(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step(q, k, v)
+        flush.fill_(1)       # evict inputs/outputs from L2 between timed iterations
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / a.steps
+    n_launch = (launches() - l0) // max(a.steps, 1)
+
+    # ------------------------------------------------------------------ end-to-end timing
+    copy_stream = torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            ts = to_dev(True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return ts, ev
+
+    results = []
+    for _ in range(2):      # warm the pipelined path
+        ts, ev = prefetch()
+        cur.wait_event(ev)
+        results.append(float(step(*ts).float().mean().item()))
+    barrier()
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    nxt = prefetch()
+    for i in range(a.steps):
+        ts, ev = nxt
+        cur.wait_event(ev)
+        for t in ts:
+            t.record_stream(cur)
+        if i + 1 < a.steps:
+            nxt = prefetch()          # H2D of step i+1 overlaps the attention of step i
+        out = step(*ts)
+        results.append(float(out.float().mean().item()))     # D2H read of the step's result
+    t_ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_e2e = t_ev0.elapsed_time(t_ev1) / a.steps
+
+    if need_dist and world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
+    if need_grad:
+        flops *= 3.5
+    tflops = flops / (ms * 1e-3) / 1e12
+    tflops_e2e = flops / (ms_e2e * 1e-3) / 1e12
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "attention_tflops_" + ("fwd_bwd" if need_grad else "fwd"),
+            "value": round(tflops, 2), "unit": "TFLOPS", "n_gpus": N, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (randn q/k/v shards, no weights in this op)",
+            "impl": a.impl,
+            "config": {"model": "LongContextAttention(ring_impl_type=%s)" % a.ring_impl, "global_batch": B,
+                       "seq_len": S, "heads": H, "kv_heads": Hkv, "head_dim": D, "causal": causal,
+                       "parallelism": f"ulysses{U}xring{R}", "mode": a.mode,
+                       "l2": "256 MiB flush write between timed iterations; per-rank q+k+v+o also exceed L2",
+                       "native_kernels": native_ok},
+            "clocks": clocks,
+            "e2e": {"value": round(tflops_e2e, 2), "unit": "TFLOPS", "ms_per_step": round(ms_e2e, 4),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(n_launch * a.steps) if a.impl == "ours" else None,
+        }))
+    if need_dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,14 +31,44 @@ def _load():
     return _C
 
 
+LAUNCHES = 0     # number of in-tree CUDA kernels launched through this module (bench.py reports it)
+_KERNEL_FUNCS = {"fmha_fwd", "fmha_bwd", "merge_out_lse", "finalize_out", "flatten_varlen_lse",
+                 "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd", "symm_barrier"}
+
+
+class _CountingExt:
+    """Proxy over the extension module that counts kernel launches."""
+
+    def __init__(self, mod):
+        self._mod = mod
+
+    def __getattr__(self, name):
+        fn = getattr(self._mod, name)
+        if name not in _KERNEL_FUNCS:
+            return fn
+
+        def wrapped(*a, **kw):
+            global LAUNCHES
+            LAUNCHES += 1
+            return fn(*a, **kw)
+
+        return wrapped
+
+
+_PROXY = None
+
+
 def ext():
+    global _PROXY
     c = _load()
     if c is None:
         raise RuntimeError(
             f"lca_b200 native extension not loadable ({_LOAD_ERROR}); build it with "
             "`python -m lca_b200.ops.build`"
         )
-    return c
+    if _PROXY is None:
+        _PROXY = _CountingExt(c)
+    return _PROXY
 
 
 def _is_blackwell(device) -> bool:

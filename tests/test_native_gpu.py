@@ -1,0 +1,155 @@
+"""GPU tests (B200): the sm_100a kernels against the fp32 PyTorch oracle of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _native():
+    from lca_b200.ops import native
+    assert native.available(), "sm_100a extension must be loadable on the GPU box (no silent fallback)"
+    return native
+
+
+def _mk(B, Sq, Sk, H, Hkv, D, dtype=torch.bfloat16, seed=0):
+    torch.manual_seed(seed)
+    return (torch.randn(B, Sq, H, D, device="cuda", dtype=dtype), torch.randn(B, Sk, Hkv, D, device="cuda", dtype=dtype),
+            torch.randn(B, Sk, Hkv, D, device="cuda", dtype=dtype))
+
+
+CASES = [
+    # B, Sq, Sk, H, Hkv, D, kwargs
+    (1, 128, 128, 1, 1, 128, {}),
+    (2, 333, 333, 3, 3, 128, dict(causal=True)),
+    (2, 200, 777, 4, 2, 64, {}),
+    (2, 1024, 1024, 8, 2, 128, dict(causal=True)),
+    (1, 1024, 1024, 2, 2, 128, dict(causal=True, window_size=(300, 0))),
+    (1, 1024, 1024, 2, 2, 64, dict(window_size=(100, 200))),
+    (1, 512, 512, 2, 2, 128, dict(causal=True, softcap=15.0)),
+    (1, 512, 512, 4, 4, 128, dict(causal=True, alibi=True)),
+    (1, 2048, 2048, 4, 1, 128, dict(causal=True)),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H,Hkv,D,kw", CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fmha_fwd_vs_oracle(B, Sq, Sk, H, Hkv, D, kw, dtype):
+    native = _native()
+    from lca_b200.ops.attention import AttnParams
+    from lca_b200.ops.ref_attention import attn_block_fwd_ref
+    from lca_b200.parallel.layout import Seg, pos_tensor
+    kw = dict(kw)
+    q, k, v = _mk(B, Sq, Sk, H, Hkv, D, dtype)
+    slopes = torch.rand(H, device="cuda") * 0.5 if kw.pop("alibi", False) else None
+    p = AttnParams.make(q, None, kw.get("causal", False), kw.get("window_size", (-1, -1)), kw.get("softcap", 0.0), slopes)
+    qp, kp = (Seg(max(Sk - Sq, 0), Sq, 1),), (Seg(0, Sk, 1),)
+    out, lse = native.fmha_fwd(q, k, v, qp, kp, p)
+    ro, rl = attn_block_fwd_ref(q, k, v, pos_tensor(qp, "cuda"), pos_tensor(kp, "cuda"), p.softmax_scale, p.causal,
+                                p.window_size, p.softcap, slopes)
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3
+    torch.testing.assert_close(out.float(), ro.float(), atol=tol, rtol=0)
+    fin = torch.isfinite(rl)
+    assert torch.equal(torch.isfinite(lse), fin)
+    torch.testing.assert_close(lse[fin], rl[fin], atol=2e-3, rtol=1e-4)
+
+
+@pytest.mark.parametrize("variant", ["basic", "zigzag", "stripe"])
+def test_fmha_fwd_ring_blocks_merge_to_whole(variant):
+    """4 simulated ring ranks on one GPU: per-block native attention with global positions + native
+    merge kernel == whole-sequence oracle (causal + window exact across blocks)."""
+    native = _native()
+    from lca_b200.ops.attention import AttnParams, merge_out_lse_
+    from lca_b200.ops.ref_attention import attention_ref
+    from lca_b200.parallel.layout import pos_tensor, ring_positions
+    R, S, H, D = 4, 2048, 4, 128
+    q, k, v = _mk(1, S, S, H, H, D)
+    p = AttnParams.make(q, None, True, (700, 0))
+    ro, rl = attention_ref(q, k, v, causal=True, window_size=(700, 0))
+    for r in range(R):
+        qpos = ring_positions(variant, r, R, S // R)
+        qi = q[:, pos_tensor(qpos, "cuda")].contiguous()
+        acc_o = acc_l = None
+        for src in range(R):
+            kpos = ring_positions(variant, src, R, S // R)
+            idx = pos_tensor(kpos, "cuda")
+            bo, bl = native.fmha_fwd(qi, k[:, idx].contiguous(), v[:, idx].contiguous(), qpos, kpos, p)
+            if acc_o is None:
+                acc_o, acc_l = bo.float(), bl
+            else:
+                merge_out_lse_(acc_o, acc_l, bo, bl)
+        torch.testing.assert_close(acc_o, ro[:, pos_tensor(qpos, "cuda")].float(), atol=2e-2, rtol=0)
+        torch.testing.assert_close(acc_l, rl[:, :, pos_tensor(qpos, "cuda")], atol=2e-3, rtol=1e-4)
+
+
+def test_varlen_groups_native():
+    native = _native()
+    from lca_b200.ops.attention import AttnParams
+    from lca_b200.ops.ref_attention import attention_ref
+    from lca_b200.parallel.layout import varlen_positions
+    lens = [300, 129, 1000, 64]
+    cu = [0]
+    for l in lens:
+        cu.append(cu[-1] + l)
+    q, k, v = _mk(1, cu[-1], cu[-1], 4, 2, 128)
+    spec = varlen_positions("basic", 0, 1, cu)
+    p = AttnParams.make(q, None, True)
+    out, lse = native.fmha_fwd(q, k, v, spec, spec, p)
+    for i, l in enumerate(lens):
+        sl = slice(cu[i], cu[i + 1])
+        ro, rl = attention_ref(q[:, sl], k[:, sl], v[:, sl], causal=True)
+        torch.testing.assert_close(out[:, sl].float(), ro.float(), atol=2e-2, rtol=0)
+        torch.testing.assert_close(lse[:, :, sl], rl, atol=2e-3, rtol=1e-4)
+
+
+def test_util_kernels():
+    native = _native()
+    C = native.ext()
+    torch.manual_seed(0)
+    B, S, H, D = 2, 257, 3, 128
+    acc = torch.randn(B, S, H, D, device="cuda")
+    la = torch.randn(B, H, S, device="cuda")
+    bo = torch.randn(B, S, H, D, device="cuda", dtype=torch.bfloat16)
+    lb = torch.randn(B, H, S, device="cuda")
+    la[0, 0, :5] = float("-inf")
+    lb[0, 0, 3:8] = float("-inf")
+    new = torch.logaddexp(la, lb)
+    safe = torch.where(torch.isinf(new), torch.zeros_like(new), new)
+    ref = acc * torch.exp(la - safe).transpose(1, 2).unsqueeze(-1) + bo.float() * torch.exp(lb - safe).transpose(1, 2).unsqueeze(-1)
+    a2, l2 = acc.clone(), la.clone()
+    C.merge_out_lse(a2, l2, bo, lb)
+    torch.testing.assert_close(a2, ref, atol=1e-4, rtol=1e-4)
+    torch.testing.assert_close(l2, new, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(C.finalize_out(acc, torch.bfloat16), acc.to(torch.bfloat16))
+    x = torch.randn(2, 5, 4, 6, 8, device="cuda", dtype=torch.bfloat16)
+    y = C.permute_group(x, 4, True)
+    assert torch.equal(y, x.permute(2, 0, 1, 3, 4).contiguous())
+    assert torch.equal(C.permute_group(y, 4, False), x)
+    o = torch.randn(2, 65, 3, 128, device="cuda", dtype=torch.bfloat16)
+    do = torch.randn_like(o)
+    torch.testing.assert_close(C.attn_delta(o, do), (o.float() * do.float()).sum(-1).permute(0, 2, 1), atol=1e-3, rtol=1e-3)
+    cu = torch.tensor([0, 3, 10, 14], device="cuda", dtype=torch.int32)
+    lse = torch.randn(3, 2, 7, device="cuda")
+    flat = C.flatten_varlen_lse(lse, cu, 14)
+    back = C.unflatten_varlen_lse(flat, cu, 7)
+    for i, (s, e) in enumerate([(0, 3), (3, 10), (10, 14)]):
+        assert torch.equal(flat[:, s:e], lse[i, :, : e - s])
+        assert torch.equal(back[i, :, : e - s], lse[i, :, : e - s])
+
+
+def test_module_single_gpu_forward_backward():
+    """Public API on one GPU: native forward, gradients vs oracle."""
+    _native()
+    import lca_b200
+    from lca_b200.kernels.attention import pytorch_attn_func
+    lca_b200.set_seq_parallel_pg(1, 1, 0, 1)
+    q, k, v = (t.requires_grad_() for t in _mk(1, 1024, 1024, 4, 2, 128))
+    attn = lca_b200.LongContextAttention(ring_impl_type="zigzag")
+    out = attn(q, k, v, causal=True)
+    do = torch.randn_like(out)
+    out.backward(do)
+    q2, k2, v2 = (t.detach().clone().requires_grad_() for t in (q, k, v))
+    ref = pytorch_attn_func(q2, k2, v2, causal=True)
+    ref.backward(do)
+    torch.testing.assert_close(out.float(), ref.float(), atol=2e-2, rtol=0)
+    for a, b in ((q.grad, q2.grad), (k.grad, k2.grad), (v.grad, v2.grad)):
+        torch.testing.assert_close(a.float(), b.float(), atol=5e-2, rtol=5e-2)
