@@ -99,11 +99,11 @@ def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
 
 
 def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
-                   engine: Optional[str] = None, dropout_mask=None, delta=None):
+                   engine: Optional[str] = None, dropout_mask=None, delta=None, lse2=None):
     """-> fp32 (dq, dk, dv) contributions of this block (see ref_attention.attn_block_bwd_ref)."""
     eng = pick_engine(q, engine)
     if eng == "native" and p.dropout_p == 0.0 and native.has_bwd():
-        return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta)
+        return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta, lse2=lse2)
     return ref_attention.attn_block_bwd_ref(
         dout, q, k, v, out, lse, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device),
         p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p,

@@ -56,7 +56,7 @@ bool encode_tmap_4d(CUtensorMap* out, const void* base, int64_t D, int64_t H, in
   return true;
 }
 
-static void make_tmap(CUtensorMap* m, const at::Tensor& t, const char* name) {
+static void make_tmap(CUtensorMap* m, const at::Tensor& t, const char* name, int box_rows = 128) {
   TORCH_CHECK(t.dim() == 4, name, " must be (B, S, H, D)");
   TORCH_CHECK(t.stride(3) == 1, name, " last dim must be contiguous");
   const int64_t B = t.size(0), S = t.size(1), H = t.size(2), D = t.size(3);
@@ -64,7 +64,7 @@ static void make_tmap(CUtensorMap* m, const at::Tensor& t, const char* name) {
   if (B == 1) sb = S * ss;           // stride of a size-1 dim is arbitrary; keep the map valid
   if (H == 1) sh = D;
   const char* err = nullptr;
-  TORCH_CHECK(encode_tmap_4d(m, t.data_ptr(), D, H, S, B, sh, ss, sb, 128, &err), name, ": ", err ? err : "?");
+  TORCH_CHECK(encode_tmap_4d(m, t.data_ptr(), D, H, S, B, sh, ss, sb, box_rows, &err), name, ": ", err ? err : "?");
 }
 
 static int dtype_code(const at::Tensor& t) {
@@ -177,6 +177,95 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                               at::cuda::getCurrentCUDAStream()));
 }
 
+// ------------------------------------------------------------------------------------ fmha bwd
+// One pass of the backward (see fmha_bwd_sm100.cu).  x0/x1 stationary, y0/y1 streamed.
+// xsegs[i] = {row0, nrows, pos0, group, o_row0};  ysegs[i] = {row0, nrows, pos0, flag, group}
+void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
+                   const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+                   int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
+                   at::Tensor& out0, const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl,
+                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit) {
+  TORCH_CHECK(x0.is_cuda() && (x0.scalar_type() == at::kBFloat16 || x0.scalar_type() == at::kHalf), "x0 must be CUDA bf16/fp16");
+  for (const at::Tensor* t : {&x1, &y0, &y1}) TORCH_CHECK(t->scalar_type() == x0.scalar_type() && t->is_cuda(), "dtype mismatch");
+  const int64_t B = x0.size(0), Hx = x0.size(2), Hy = y0.size(2), D = x0.size(3);
+  TORCH_CHECK(D == 64 || D == 128, "head_dim must be 64 or 128");
+  TORCH_CHECK(x1.sizes() == x0.sizes() && y1.sizes() == y0.sizes() && y0.size(0) == B && y0.size(3) == D, "shape mismatch");
+  TORCH_CHECK(!xsegs.empty() && xsegs.size() <= kMaxSeg && !ysegs.empty() && ysegs.size() <= kMaxSeg, "segment count");
+  const int64_t Hq = is_dkv ? Hy : Hx;
+  TORCH_CHECK(is_dkv ? (Hy % Hx == 0) : (Hx % Hy == 0), "head counts");
+  TORCH_CHECK(lse2.scalar_type() == at::kFloat && delta.scalar_type() == at::kFloat && lse2.dim() == 3 &&
+              lse2.sizes() == delta.sizes() && lse2.stride(2) == 1 && delta.strides() == lse2.strides(), "lse2/delta");
+  TORCH_CHECK(lse2.size(0) == B && lse2.size(1) == Hq, "lse2 shape");
+  c10::cuda::CUDAGuard guard(x0.device());
+  BwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  make_tmap(&p.tm_x0, x0, "x0", 128);
+  make_tmap(&p.tm_x1, x1, "x1", 128);
+  make_tmap(&p.tm_y0, y0, "y0", 64);
+  make_tmap(&p.tm_y1, y1, "y1", 64);
+  p.n_xseg = static_cast<int>(xsegs.size());
+  p.n_yseg = static_cast<int>(ysegs.size());
+  int64_t tiles = 0;
+  for (int i = 0; i < p.n_xseg; ++i) {
+    const auto& s = xsegs[i];
+    TORCH_CHECK(s.size() == 5 && s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= x0.size(1), "bad xseg");
+    TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out0.size(1), "xseg output rows out of range");
+    p.xseg[i] = {static_cast<int>(s[0]), static_cast<int>(s[1]), static_cast<int>(s[2]), static_cast<int>(s[3]),
+                 static_cast<int>(s[4]), 0};
+    tiles += (s[1] + 127) / 128;
+  }
+  for (int i = 0; i < p.n_yseg; ++i) {
+    const auto& s = ysegs[i];
+    TORCH_CHECK(s.size() == 5 && s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= y0.size(1), "bad yseg");
+    p.yseg[i] = {static_cast<int>(s[0]), static_cast<int>(s[1]), static_cast<int>(s[2]), static_cast<int>(s[3]),
+                 static_cast<int>(s[4])};
+  }
+  p.x_pos_stride = static_cast<int>(x_pos_stride);
+  p.y_pos_stride = static_cast<int>(y_pos_stride);
+  p.x_heavy_last = is_dkv ? 0 : 1;
+  p.B = static_cast<int>(B);
+  p.Hx = static_cast<int>(Hx);
+  p.n_inner = is_dkv ? static_cast<int>(Hy / Hx) : 1;
+  p.hx_per_hy = is_dkv ? 1 : static_cast<int>(Hx / Hy);
+  p.total_work = static_cast<int>(tiles * B * Hx);
+  p.wl = static_cast<int>(wl);
+  p.wr = static_cast<int>(wr);
+  p.scale = static_cast<float>(scale);
+  p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
+  p.softcap = static_cast<float>(softcap);
+  if (alibi.has_value() && alibi->defined()) {
+    const at::Tensor& a = *alibi;
+    TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat && a.is_contiguous(), "alibi_slopes must be fp32 CUDA contiguous");
+    TORCH_CHECK((a.dim() == 1 && a.size(0) == Hq) || (a.dim() == 2 && a.size(0) == B && a.size(1) == Hq), "alibi shape");
+    p.alibi = a.data_ptr<float>();
+    p.alibi_bstride = a.dim() == 2 ? static_cast<int>(Hq) : 0;
+  }
+  p.lse2 = lse2.data_ptr<float>();
+  p.delta = delta.data_ptr<float>();
+  p.stat_sb = lse2.stride(0);
+  p.stat_sh = lse2.stride(1);
+  TORCH_CHECK(out0.dim() == 4 && out0.size(0) == B && out0.size(2) == Hx && out0.size(3) == D && out0.stride(3) == 1, "out0 shape");
+  const bool f32 = out0.scalar_type() == at::kFloat;
+  TORCH_CHECK(f32 || out0.scalar_type() == x0.scalar_type(), "out dtype");
+  TORCH_CHECK(!accumulate || f32, "accumulate needs fp32 outputs");
+  p.out0 = out0.data_ptr();
+  p.o_sb = out0.stride(0);
+  p.o_ss = out0.stride(1);
+  p.o_sh = out0.stride(2);
+  TORCH_CHECK(p.o_ss % 8 == 0 && p.o_sh % 8 == 0 && reinterpret_cast<uintptr_t>(p.out0) % 16 == 0, "out0 alignment");
+  if (is_dkv) {
+    TORCH_CHECK(out1.has_value() && out1->sizes() == out0.sizes() && out1->strides() == out0.strides() &&
+                out1->scalar_type() == out0.scalar_type(), "out1 must match out0");
+    p.out1 = out1->data_ptr();
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(p.out1) % 16 == 0, "out1 alignment");
+  }
+  p.out_mode = f32 ? (accumulate ? 2 : 1) : 0;
+  int sms = num_sms();
+  if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(D), x0.scalar_type() == at::kBFloat16, is_dkv, sms,
+                              at::cuda::getCurrentCUDAStream()));
+}
+
 // ------------------------------------------------------------------------------------ utilities
 void merge_out_lse(at::Tensor& out_acc, at::Tensor& lse_acc, const at::Tensor& block_out, const at::Tensor& block_lse) {
   TORCH_CHECK(out_acc.is_cuda() && out_acc.scalar_type() == at::kFloat && out_acc.is_contiguous() && out_acc.dim() == 4);
@@ -251,16 +340,28 @@ at::Tensor permute_group(const at::Tensor& src, int64_t G, bool to_group_major) 
   return dst;
 }
 
-at::Tensor attn_delta(const at::Tensor& out, const at::Tensor& dout) {
+// delta = rowsum(out o dout) (B,H,S); with `lse` also returns the log2-domain LSE the backward kernels read
+std::vector<at::Tensor> attn_delta(const at::Tensor& out, const at::Tensor& dout, const c10::optional<at::Tensor>& lse) {
   TORCH_CHECK(out.is_cuda() && out.dim() == 4 && out.sizes() == dout.sizes() && out.scalar_type() == dout.scalar_type());
   TORCH_CHECK(out.stride(3) == 1 && dout.stride(3) == 1);
   const int B = out.size(0), S = out.size(1), H = out.size(2), D = out.size(3);
   at::Tensor delta = at::empty({B, H, S}, out.options().dtype(at::kFloat));
+  at::Tensor lse2;
+  const float* lse_p = nullptr;
+  float* lse2_p = nullptr;
+  if (lse.has_value() && lse->defined()) {
+    TORCH_CHECK(lse->scalar_type() == at::kFloat && lse->is_contiguous() && lse->dim() == 3 && lse->size(0) == B &&
+                lse->size(1) == H && lse->size(2) == S, "lse must be contiguous (B,H,S) fp32");
+    lse2 = at::empty({B, H, S}, delta.options());
+    lse_p = lse->data_ptr<float>();
+    lse2_p = lse2.data_ptr<float>();
+  }
   c10::cuda::CUDAGuard guard(out.device());
-  LCA_CUDA_OK(launch_delta(out.data_ptr(), dout.data_ptr(), dtype_code(out), delta.data_ptr<float>(), B, S, H, D,
-                           out.stride(0), out.stride(1), out.stride(2), dout.stride(0), dout.stride(1), dout.stride(2),
+  LCA_CUDA_OK(launch_delta(out.data_ptr(), dout.data_ptr(), dtype_code(out), delta.data_ptr<float>(), lse_p, lse2_p, B, S, H,
+                           D, out.stride(0), out.stride(1), out.stride(2), dout.stride(0), dout.stride(1), dout.stride(2),
                            at::cuda::getCurrentCUDAStream()));
-  return delta;
+  if (lse2.defined()) return {delta, lse2};
+  return {delta};
 }
 
 }  // namespace lca
@@ -268,6 +369,7 @@ at::Tensor attn_delta(const at::Tensor& out, const at::Tensor& dout) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lca_b200 sm_100a kernels";
   m.def("fmha_fwd", &lca::fmha_fwd, "tcgen05 flash-attention forward (segments + global positions)");
+  m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
   m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");
   m.def("finalize_out", &lca::finalize_out, "fp32 accumulator -> 16-bit output");
   m.def("flatten_varlen_lse", &lca::flatten_varlen_lse);

@@ -1,0 +1,532 @@
+// Backward flash attention for sm_100a (B200): two tcgen05 passes sharing ONE kernel template.
+//
+//   pass dQ  (kIsDKV = false): stationary X = (Q_i, dO_i) tile of 128 query rows on the TMEM lanes,
+//            streamed   Y = (K_j, V_j) tiles of 64 key rows.
+//              T0 = Q K^T, T1 = dO V^T            (SS MMAs, fp32 in TMEM, double buffered)
+//              P  = exp2(T0*scale*log2e - lse2_row), dS = P o (T1 - delta_row)   (softmax warpgroups)
+//              dQ += dS K                          (TS MMA: A = dS from TMEM, B = K as MN-major smem)
+//   pass dKV (kIsDKV = true):  stationary X = (K_j, V_j) tile of 128 key rows on the lanes,
+//            streamed   Y = (Q_i, dO_i) tiles of 64 query rows (+ their lse2/delta columns),
+//            looped over the G = H/Hkv query heads of the KV head (GQA reduces inside TMEM).
+//              T0 = K Q^T (= S^T), T1 = V dO^T (= dP^T)
+//              P^T, dS^T as above with per-COLUMN lse2/delta
+//              dK += dS^T Q,  dV += P^T dO         (TS MMAs)
+// Both passes are deterministic (no atomics: every output element is owned by one CTA) and use the
+// same segment/global-position masking as the forward kernel; for the dKV pass the host swaps
+// the window bounds because rows are keys and columns are queries.
+// Seven GEMMs instead of the five of a fused dQ/dK/dV kernel, but nothing leaves TMEM between
+// them, no fp32 dQ atomics cross L2, and TMEM (512 columns) is never oversubscribed:
+//   [0,128) T0 x2 stages | [128,256) T1 x2 stages | [256,256+D) acc0 | [256+D,256+2D) acc1.
+//
+// Capability parity: flash_attn::_flash_attn_backward as called from
+// yunchang/kernels/attention.py:205-250 (dq/dk/dv from dout,q,k,v,out,lse).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "fmha_params.h"
+#include "sm100_ptx.cuh"
+
+namespace lca {
+using namespace ptx;
+
+namespace {
+
+constexpr int BX = 128;   // stationary rows (TMEM lanes)
+constexpr int BY = 64;    // streamed rows per tile (TMEM columns of T0/T1)
+constexpr int kThreads = 384;
+constexpr int kMmaWarp = 8;
+constexpr int kTmaWarp = 9;
+
+template <int kD>
+struct Cfg {
+  static constexpr int DBLK = kD / 64;
+  static constexpr int XBLK_BYTES = BX * 128;             // [128 rows][64 elem]
+  static constexpr int YBLK_BYTES = BY * 128;             // [64 rows][64 elem]
+  static constexpr int XTILE_BYTES = DBLK * XBLK_BYTES;   // one stationary operand
+  static constexpr int YTILE_BYTES = DBLK * YBLK_BYTES;   // one streamed operand
+  static constexpr int STAGES = 4;                        // streamed (Y0,Y1) tile pairs in flight
+  static constexpr int OFF_X = 0;
+  static constexpr int OFF_Y = 2 * XTILE_BYTES;
+  static constexpr int OFF_STAT = OFF_Y + STAGES * 2 * YTILE_BYTES;   // per stage: lse2[64], delta[64]
+  static constexpr int OFF_BAR = OFF_STAT + STAGES * 2 * BY * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+  static constexpr int TMEM_T0 = 0, TMEM_T1 = 128, TMEM_ACC0 = 256, TMEM_ACC1 = 256 + kD;
+};
+
+struct Work {
+  int xseg, seg_row0, row0, nrows, pos0, b, hx;
+};
+
+__device__ __forceinline__ bool decode_work(const BwdParams& p, int w, Work& wk) {
+  if (w >= p.total_work) return false;
+  const int bh = p.B * p.Hx;
+  int t = w / bh;
+  const int r = w - t * bh;
+  wk.b = r / p.Hx;
+  wk.hx = r - wk.b * p.Hx;
+  for (int s = 0; s < p.n_xseg; ++s) {
+    const int nt = (p.xseg[s].nrows + BX - 1) / BX;
+    if (t < nt) {
+      const int ti = p.x_heavy_last ? (nt - 1 - t) : t;
+      wk.xseg = s;
+      wk.seg_row0 = ti * BX;
+      wk.row0 = p.xseg[s].row0 + wk.seg_row0;
+      wk.nrows = min(BX, p.xseg[s].nrows - wk.seg_row0);
+      wk.pos0 = p.xseg[s].pos0 + wk.seg_row0 * p.x_pos_stride;
+      return true;
+    }
+    t -= nt;
+  }
+  return false;
+}
+
+__device__ __forceinline__ int sched_work(int round) {
+  const int G = gridDim.x;
+  const int c = (round & 1) ? (G - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
+  return round * G + c;
+}
+
+// streamed-tile enumeration: (inner head gi) x (segment) x (64-row tile), skipping tiles that are
+// entirely masked for the stationary tile's position range.  Identical in every warp role.
+struct TileIter {
+  int gi, seg, yt;
+  int xmin, xmax, xgroup;
+  int y_row0, nvalid, ypos0, flag;
+  __device__ __forceinline__ void init(const BwdParams& p, const Work& wk) {
+    gi = 0; seg = 0; yt = -1;
+    xmin = wk.pos0;
+    xmax = wk.pos0 + (wk.nrows - 1) * p.x_pos_stride;
+    xgroup = p.xseg[wk.xseg].group;
+  }
+  __device__ __forceinline__ bool next(const BwdParams& p) {
+    while (gi < p.n_inner) {
+      while (seg < p.n_yseg) {
+        const KSegD s = p.yseg[seg];
+        const int nt = (s.group == xgroup) ? (s.nrows + BY - 1) / BY : 0;
+        while (++yt < nt) {
+          const int r0 = yt * BY;
+          const int nv = min(BY, s.nrows - r0);
+          const int ya = s.pos0 + r0 * p.y_pos_stride;
+          const int yb = ya + (nv - 1) * p.y_pos_stride;
+          if (p.wr >= 0 && ya - xmax > p.wr) break;
+          if (p.wl >= 0 && xmin - yb > p.wl) continue;
+          y_row0 = s.row0 + r0; nvalid = nv; ypos0 = ya; flag = s.flag;
+          return true;
+        }
+        ++seg; yt = -1;
+      }
+      ++gi; seg = 0; yt = -1;
+    }
+    return false;
+  }
+};
+
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
+
+// write one row-slice of an accumulator: 32 fp32 values -> out (mode 0: 16-bit, 1: fp32 store, 2: fp32 +=)
+template <bool kBf16>
+__device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t (&o)[32], float mul, int mode) {
+  if (mode == 0) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(base) + col0 * 2);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 w;
+      w.x = pack2<kBf16>(__uint_as_float(o[g * 8 + 0]) * mul, __uint_as_float(o[g * 8 + 1]) * mul);
+      w.y = pack2<kBf16>(__uint_as_float(o[g * 8 + 2]) * mul, __uint_as_float(o[g * 8 + 3]) * mul);
+      w.z = pack2<kBf16>(__uint_as_float(o[g * 8 + 4]) * mul, __uint_as_float(o[g * 8 + 5]) * mul);
+      w.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * mul, __uint_as_float(o[g * 8 + 7]) * mul);
+      dst[g] = w;
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(base) + col0 * 4);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float4 w = make_float4(__uint_as_float(o[g * 4 + 0]) * mul, __uint_as_float(o[g * 4 + 1]) * mul,
+                             __uint_as_float(o[g * 4 + 2]) * mul, __uint_as_float(o[g * 4 + 3]) * mul);
+      if (mode == 2) {
+        const float4 old = dst[g];
+        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+      }
+      dst[g] = w;
+    }
+  }
+}
+
+}  // namespace
+
+template <int kD, bool kBf16, bool kIsDKV>
+__global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
+  using C = Cfg<kD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- barriers
+  uint32_t a = smem + C::OFF_BAR;
+  const uint32_t x_full = a; a += 8;
+  const uint32_t x_empty = a; a += 8;
+  const uint32_t acc_full = a; a += 8;
+  const uint32_t acc_empty = a; a += 8;
+  const uint32_t t_full = a; a += 16;      // [2]
+  const uint32_t p_full = a; a += 16;      // [2]
+  const uint32_t y_full = a; a += 8 * C::STAGES;
+  const uint32_t y_empty = a; a += 8 * C::STAGES;
+  const uint32_t st_full = a; a += 8 * C::STAGES;
+  const uint32_t st_empty = a; a += 8 * C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::OFF_BAR + 480);
+  float* stat = reinterpret_cast<float*>(smem_gen + C::OFF_STAT);
+
+  if (threadIdx.x == 0) {
+    mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(t_full + 8 * s, 1);
+      mbar_init(p_full + 8 * s, 4);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(y_full + 8 * s, 1);
+      mbar_init(y_empty + 8 * s, 1);
+      mbar_init(st_full + 8 * s, 32);
+      mbar_init(st_empty + 8 * s, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kTmaWarp && lane == 0) {
+    prefetch_tmap(&p.tm_x0); prefetch_tmap(&p.tm_x1); prefetch_tmap(&p.tm_y0); prefetch_tmap(&p.tm_y1);
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= kMmaWarp) {
+    setmaxnreg_dec<96>();
+    if (warp == kTmaWarp) {
+      // =========================================================== producer (whole warp: lane 0 drives TMA,
+      // all lanes fetch the per-column lse2/delta of streamed query tiles in the dKV pass)
+      uint32_t xc = 0, yc = 0;
+      for (int round = 0;; ++round) {
+        Work wk;
+        if (!decode_work(p, sched_work(round), wk)) break;
+        if (lane == 0) {
+          mbar_wait(x_empty, (xc & 1) ^ 1);
+          mbar_arrive_expect_tx(x_full, 2 * C::XTILE_BYTES);
+#pragma unroll
+          for (int db = 0; db < C::DBLK; ++db) {
+            tma_load_4d(smem + C::OFF_X + db * C::XBLK_BYTES, &p.tm_x0, x_full, db * 64, wk.hx, wk.row0, wk.b);
+            tma_load_4d(smem + C::OFF_X + C::XTILE_BYTES + db * C::XBLK_BYTES, &p.tm_x1, x_full, db * 64, wk.hx, wk.row0, wk.b);
+          }
+        }
+        ++xc;
+        TileIter it;
+        it.init(p, wk);
+        while (it.next(p)) {
+          const int hy = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx / p.hx_per_hy;
+          const uint32_t st = yc % C::STAGES;
+          const uint32_t par = (yc / C::STAGES) & 1;
+          if (lane == 0) {
+            mbar_wait(y_empty + 8 * st, par ^ 1);
+            mbar_arrive_expect_tx(y_full + 8 * st, 2 * C::YTILE_BYTES);
+#pragma unroll
+            for (int db = 0; db < C::DBLK; ++db) {
+              tma_load_4d(smem + C::OFF_Y + st * 2 * C::YTILE_BYTES + db * C::YBLK_BYTES, &p.tm_y0, y_full + 8 * st,
+                          db * 64, hy, it.y_row0, wk.b);
+              tma_load_4d(smem + C::OFF_Y + st * 2 * C::YTILE_BYTES + C::YTILE_BYTES + db * C::YBLK_BYTES, &p.tm_y1,
+                          y_full + 8 * st, db * 64, hy, it.y_row0, wk.b);
+            }
+          }
+          if constexpr (kIsDKV) {
+            mbar_wait(st_empty + 8 * st, par ^ 1);
+            const float* l2 = p.lse2 + wk.b * p.stat_sb + hy * p.stat_sh;
+            const float* dl = p.delta + wk.b * p.stat_sb + hy * p.stat_sh;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int c = lane + 32 * i;
+              const bool ok = c < it.nvalid;
+              stat[st * 2 * BY + c] = ok ? l2[it.y_row0 + c] : INFINITY;
+              stat[st * 2 * BY + BY + c] = ok ? dl[it.y_row0 + c] : 0.f;
+            }
+            mbar_arrive(st_full + 8 * st);
+          }
+          ++yc;
+        }
+      }
+    } else if (warp == kMmaWarp) {
+      // =========================================================== MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc_t = make_idesc_f16(kBf16 ? 1 : 0, BX, BY, 0, 0);
+        constexpr uint32_t idesc_acc = make_idesc_f16(kBf16 ? 1 : 0, BX, kD, 0, 1);
+        uint32_t xc = 0, yc = 0, pc[2] = {0, 0}, ac = 0;
+        auto issue_t = [&](uint32_t stage, int s) {
+          const uint32_t x0 = smem + C::OFF_X, x1 = x0 + C::XTILE_BYTES;
+          const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t xo = (kk >> 2) * C::XBLK_BYTES + (kk & 3) * 32;
+            const uint32_t yo = (kk >> 2) * C::YBLK_BYTES + (kk & 3) * 32;
+            mma_ss(tmem + C::TMEM_T0 + s * BY, make_sw128_desc(x0 + xo, 16, 1024), make_sw128_desc(y0 + yo, 16, 1024),
+                   idesc_t, kk > 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint32_t xo = (kk >> 2) * C::XBLK_BYTES + (kk & 3) * 32;
+            const uint32_t yo = (kk >> 2) * C::YBLK_BYTES + (kk & 3) * 32;
+            mma_ss(tmem + C::TMEM_T1 + s * BY, make_sw128_desc(x1 + xo, 16, 1024), make_sw128_desc(y1 + yo, 16, 1024),
+                   idesc_t, kk > 0 ? 1u : 0u);
+          }
+        };
+        auto issue_acc = [&](uint32_t stage, int s, bool acc) {
+          const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BY / 16; ++kk)   // acc0 += dS * Y0
+            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + kk * 8,
+                   make_sw128_desc(y0 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+          if constexpr (kIsDKV) {
+#pragma unroll
+            for (int kk = 0; kk < BY / 16; ++kk)   // acc1 += P * Y1
+              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + kk * 8,
+                     make_sw128_desc(y1 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+          }
+        };
+        for (int round = 0;; ++round) {
+          Work wk;
+          if (!decode_work(p, sched_work(round), wk)) break;
+          TileIter it;
+          it.init(p, wk);
+          mbar_wait(x_full, xc & 1);
+          ++xc;
+          bool have = it.next(p);
+          if (!have) {
+            mma_commit(x_empty);
+            continue;
+          }
+          tc_fence_after();
+          // prologue: T(0) and, if present, T(1)
+          uint32_t stage_q[2];
+          int n_issued = 0;
+          bool more = have;
+          for (int s = 0; s < 2 && more; ++s) {
+            const uint32_t st = yc % C::STAGES;
+            mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
+            ++yc;
+            tc_fence_after();
+            issue_t(st, s);
+            mma_commit(t_full + 8 * s);
+            stage_q[s] = st;
+            ++n_issued;
+            more = it.next(p);
+          }
+          if (!more) mma_commit(x_empty);          // all T GEMMs (the only readers of X) are issued
+          for (int j = 0; j < n_issued; ++j) {
+            const int s = j & 1;
+            mbar_wait(p_full + 8 * s, pc[s] & 1);
+            ++pc[s];
+            if (j == 0) {
+              mbar_wait(acc_empty, (ac & 1) ^ 1);
+              ++ac;
+            }
+            tc_fence_after();
+            issue_acc(stage_q[s], s, j > 0);
+            mma_commit(y_empty + 8 * stage_q[s]);
+            if (more) {
+              const uint32_t st = yc % C::STAGES;
+              mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
+              ++yc;
+              tc_fence_after();
+              issue_t(st, s);
+              mma_commit(t_full + 8 * s);
+              stage_q[s] = st;
+              ++n_issued;
+              more = it.next(p);
+              if (!more) mma_commit(x_empty);
+            }
+          }
+          mma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    setmaxnreg_inc<200>();
+    // =========================================================== elementwise warpgroups (stage = wg)
+    const int wg = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tT0 = tmem + lane_base + C::TMEM_T0 + wg * BY;
+    const uint32_t tT1 = tmem + lane_base + C::TMEM_T1 + wg * BY;
+    uint32_t tc = 0, yc = 0, afc = 0;
+    const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
+    for (int round = 0;; ++round) {
+      Work wk;
+      if (!decode_work(p, sched_work(round), wk)) break;
+      const int xpos = wk.pos0 + row * p.x_pos_stride;
+      const int xhi = wk.pos0 + (BX - 1) * p.x_pos_stride;
+      const bool row_ok = row < wk.nrows;
+      float lse2_r = INFINITY, delta_r = 0.f;
+      if constexpr (!kIsDKV) {
+        if (row_ok) {
+          lse2_r = p.lse2[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
+          delta_r = p.delta[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
+        }
+      }
+      TileIter it;
+      it.init(p, wk);
+      int j = 0;
+      while (it.next(p)) {
+        const uint32_t st = yc % C::STAGES;
+        const uint32_t ypar = (yc / C::STAGES) & 1;
+        ++yc;
+        if ((j & 1) != wg) { ++j; continue; }
+        const int hq = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx;     // query head (ALiBi slope index)
+        const float slope = p.alibi ? p.alibi[wk.b * p.alibi_bstride + hq] : 0.f;
+        mbar_wait(t_full + 8 * wg, tc & 1);
+        ++tc;
+        if constexpr (kIsDKV) mbar_wait(st_full + 8 * st, ypar);
+        tc_fence_after();
+        const int yb = it.ypos0 + (it.nvalid - 1) * p.y_pos_stride;
+        const bool need_mask = (it.nvalid < BY) || (p.wr >= 0 && yb - wk.pos0 > p.wr) ||
+                               (p.wl >= 0 && xhi - it.ypos0 > p.wl) || (wk.nrows < BX);
+        const float* st_l2 = stat + st * 2 * BY;
+        const float* st_dl = st_l2 + BY;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t t0[32], t1[32];
+          tmem_ld32(tT0 + half * 32, t0);
+          tmem_ld32(tT1 + half * 32, t1);
+          tmem_wait_ld();
+          uint32_t pp[16], ds[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float pv[2], dv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = half * 32 + c + e;
+              const float l2 = kIsDKV ? st_l2[col] : lse2_r;
+              const float dl = kIsDKV ? st_dl[col] : delta_r;
+              const float s_raw = __uint_as_float(t0[c + e]);
+              float pe, extra = 1.f;
+              bool masked = false;
+              if (plain && !need_mask) {
+                pe = ex2(fmaf(s_raw, p.scale_log2, -l2));
+              } else {
+                float x = s_raw * p.scale;
+                if (p.softcap > 0.f) {
+                  const float th = tanh_approx(x / p.softcap);
+                  x = p.softcap * th;
+                  extra = 1.f - th * th;
+                }
+                const int rel = it.ypos0 + col * p.y_pos_stride - xpos;
+                if (p.alibi) x -= slope * fabsf(static_cast<float>(rel));
+                masked = (col >= it.nvalid) || !row_ok || (p.wr >= 0 && rel > p.wr) || (p.wl >= 0 && -rel > p.wl);
+                pe = masked ? 0.f : ex2(fmaf(x, 1.4426950408889634f, -l2));
+              }
+              pv[e] = pe;
+              dv[e] = masked ? 0.f : pe * (__uint_as_float(t1[c + e]) - dl) * extra;   // never 0 * garbage
+            }
+            pp[c >> 1] = pack2<kBf16>(pv[0], pv[1]);
+            ds[c >> 1] = pack2<kBf16>(dv[0], dv[1]);
+          }
+          if constexpr (kIsDKV) tmem_st16(tT0 + half * 16, pp);
+          tmem_st16(tT1 + half * 16, ds);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(p_full + 8 * wg);
+          if constexpr (kIsDKV) mbar_arrive(st_empty + 8 * st);
+        }
+        ++j;
+      }
+      // ---- epilogue: both warpgroups drain the accumulators (dQ: column halves; dKV: wg0 -> dK, wg1 -> dV)
+      if (j > 0) {
+        mbar_wait(acc_full, afc & 1);
+        ++afc;
+        tc_fence_after();
+      }
+      {
+        const XSegD xs = p.xseg[wk.xseg];
+        const int64_t orow = static_cast<int64_t>(xs.o_row0) + wk.seg_row0 + row;
+        int ncols, col_begin;
+        uint32_t tacc;
+        uint8_t* obase;
+        float mul;
+        int esz = (p.out_mode == 0) ? 2 : 4;
+        if constexpr (kIsDKV) {
+          ncols = kD; col_begin = 0;
+          tacc = tmem + lane_base + (wg == 0 ? C::TMEM_ACC0 : C::TMEM_ACC1);
+          obase = reinterpret_cast<uint8_t*>(wg == 0 ? p.out0 : p.out1);
+          mul = wg == 0 ? p.scale : 1.f;
+        } else {
+          ncols = kD / 2; col_begin = wg * (kD / 2);
+          tacc = tmem + lane_base + C::TMEM_ACC0;
+          obase = reinterpret_cast<uint8_t*>(p.out0);
+          mul = p.scale;
+        }
+        uint8_t* orow_ptr = obase + esz * (wk.b * p.o_sb + orow * p.o_ss + static_cast<int64_t>(wk.hx) * p.o_sh);
+        for (int c = 0; c < ncols; c += 32) {
+          uint32_t o[32];
+          if (j > 0) {
+            tmem_ld32(tacc + col_begin + c, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
+          }
+          if (row_ok) store_slice<kBf16>(orow_ptr, col_begin + c, o, mul, p.out_mode);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && j > 0) mbar_arrive(acc_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int kD, bool kBf16, bool kIsDKV>
+static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<kD>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int grid = p.total_work < num_sms ? p.total_work : num_sms;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fmha_bwd(const BwdParams& p, int head_dim, bool bf16, bool is_dkv, int num_sms, cudaStream_t stream) {
+#define LCA_DISPATCH(D, BF)                                                                 \
+  return is_dkv ? launch_impl<D, BF, true>(p, num_sms, stream) : launch_impl<D, BF, false>(p, num_sms, stream)
+  if (head_dim == 128) { if (bf16) { LCA_DISPATCH(128, true); } else { LCA_DISPATCH(128, false); } }
+  if (head_dim == 64) { if (bf16) { LCA_DISPATCH(64, true); } else { LCA_DISPATCH(64, false); } }
+#undef LCA_DISPATCH
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace lca

@@ -53,4 +53,41 @@ struct FwdParams {
   uint32_t flag_epoch;
 };
 
+// ---- backward -----------------------------------------------------------------------------------
+struct XSegD {
+  int row0;      // first row of the segment in the stationary tensors
+  int nrows;
+  int pos0;
+  int group;
+  int o_row0;    // first destination row in out0/out1
+  int pad;
+};
+
+// One parameter block serves both passes (see fmha_bwd_sm100.cu):
+//   dQ  pass: X = (Q, dO)  [Hx = H],   Y = (K, V)  [Hy = Hkv], n_inner = 1,  hx_per_hy = H/Hkv
+//   dKV pass: X = (K, V)   [Hx = Hkv], Y = (Q, dO) [Hy = H],   n_inner = H/Hkv (query heads per KV head)
+struct BwdParams {
+  CUtensorMap tm_x0, tm_x1;           // box (64,1,128,1)
+  CUtensorMap tm_y0, tm_y1;           // box (64,1,64,1)
+  int n_xseg, n_yseg;
+  XSegD xseg[kMaxSeg];
+  KSegD yseg[kMaxSeg];
+  int x_pos_stride, y_pos_stride;
+  int x_heavy_last;                   // 1: later stationary tiles cost more (walk them first)
+  int B, Hx;
+  int n_inner, hx_per_hy;
+  int total_work;
+  int wl, wr;                         // bounds on (ypos - xpos): visible iff -wl <= ypos - xpos <= wr
+  float scale, scale_log2, softcap;
+  const float* alibi;                 // indexed by QUERY head
+  int alibi_bstride;
+  const float* lse2;                  // (B, H, Sq) log2-domain LSE (+inf for empty rows), indexed by query row
+  const float* delta;                 // (B, H, Sq) rowsum(dO o O)
+  int64_t stat_sb, stat_sh;
+  void* out0;                         // dQ (dQ pass) / dK (dKV pass)
+  void* out1;                         // dV (dKV pass)
+  int64_t o_sb, o_ss, o_sh;           // output strides in elements
+  int out_mode;                       // 0: 16-bit store, 1: fp32 store, 2: fp32 accumulate
+};
+
 }  // namespace lca

@@ -11,6 +11,9 @@ namespace lca {
 // fmha_fwd_sm100.cu
 cudaError_t launch_fmha_fwd(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream);
 
+// fmha_bwd_sm100.cu
+cudaError_t launch_fmha_bwd(const BwdParams& p, int head_dim, bool bf16, bool is_dkv, int num_sms, cudaStream_t stream);
+
 // util_kernels.cu
 cudaError_t launch_merge_out_lse(float* out_acc, float* lse_acc, const void* block_out, int block_dtype /*0 f32,1 bf16,2 f16*/,
                                  const float* block_lse, int B, int S, int H, int D, cudaStream_t stream);
@@ -22,7 +25,8 @@ cudaError_t launch_unflatten_lse(const float* lse_flat, float* lse_padded, const
 // (B, S, G, Hl, D) <-> (G, B, S, Hl, D)-style head/sequence permutes used around the NCCL all-to-all
 cudaError_t launch_permute_heads_out(const void* src, void* dst, int B, int S, int G, int HlD_bytes, cudaStream_t stream);
 cudaError_t launch_permute_heads_in(const void* src, void* dst, int B, int S, int G, int HlD_bytes, cudaStream_t stream);
-cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* delta, int B, int S, int H, int D,
+cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* delta, const float* lse, float* lse2,
+                         int B, int S, int H, int D,
                          int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t do_sb, int64_t do_ss, int64_t do_sh,
                          cudaStream_t stream);
 

@@ -139,7 +139,7 @@ __global__ void permute_kernel(const uint4* __restrict__ src, uint4* __restrict_
 // delta[b,h,s] = sum_d out[b,s,h,d] * dout[b,s,h,d]; one warp per (b,s,h)
 template <typename T>
 __global__ void delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
-                             int B, int S, int H, int D, int64_t o_sb, int64_t o_ss, int64_t o_sh,
+                             const float* __restrict__ lse, float* __restrict__ lse2, int B, int S, int H, int D, int64_t o_sb, int64_t o_ss, int64_t o_sh,
                              int64_t d_sb, int64_t d_ss, int64_t d_sh) {
   const int lane = threadIdx.x & 31;
   const int64_t nrows = static_cast<int64_t>(B) * S * H;
@@ -162,7 +162,14 @@ __global__ void delta_kernel(const T* __restrict__ out, const T* __restrict__ do
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * S + s] = acc;
+    if (lane == 0) {
+      const int64_t idx = (static_cast<int64_t>(b) * H + h) * S + s;
+      delta[idx] = acc;
+      if (lse2 != nullptr) {   // log2-domain LSE for the backward kernels; rows without keys -> +inf => P = 0
+        const float l = lse[idx];
+        lse2[idx] = (l == -INFINITY) ? INFINITY : l * 1.4426950408889634f;
+      }
+    }
   }
 }
 
@@ -227,7 +234,8 @@ cudaError_t launch_permute_heads_in(const void* src, void* dst, int B, int S, in
   return cudaGetLastError();
 }
 
-cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* delta, int B, int S, int H, int D,
+cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* delta, const float* lse, float* lse2,
+                         int B, int S, int H, int D,
                          int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t d_sb, int64_t d_ss, int64_t d_sh,
                          cudaStream_t stream) {
   if (D % 8) return cudaErrorInvalidValue;
@@ -235,9 +243,9 @@ cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* de
   const int threads = 256;
   const int grid = grid_for(nrows * 32, threads);
   if (dtype == 1)
-    delta_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
+    delta_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), delta, lse, lse2, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
   else
-    delta_kernel<__half><<<grid, threads, 0, stream>>>(static_cast<const __half*>(out), static_cast<const __half*>(dout), delta, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
+    delta_kernel<__half><<<grid, threads, 0, stream>>>(static_cast<const __half*>(out), static_cast<const __half*>(dout), delta, lse, lse2, B, S, H, D, o_sb, o_ss, o_sh, d_sb, d_ss, d_sh);
   return cudaGetLastError();
 }
 

@@ -32,7 +32,7 @@ def _load():
 
 
 LAUNCHES = 0     # number of in-tree CUDA kernels launched through this module (bench.py reports it)
-_KERNEL_FUNCS = {"fmha_fwd", "fmha_bwd", "merge_out_lse", "finalize_out", "flatten_varlen_lse",
+_KERNEL_FUNCS = {"fmha_fwd", "fmha_bwd_pass", "merge_out_lse", "finalize_out", "flatten_varlen_lse",
                  "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd", "symm_barrier"}
 
 
@@ -113,7 +113,7 @@ def supports(q: torch.Tensor) -> bool:
 
 def has_bwd() -> bool:
     c = _load()
-    return c is not None and hasattr(c, "fmha_bwd")
+    return c is not None and hasattr(c, "fmha_bwd_pass") and os.environ.get("LCA_B200_TORCH_BWD", "0") != "1"
 
 
 # ------------------------------------------------------------------------------------------
@@ -200,8 +200,47 @@ def _chunk_by_group(qrows, krows):
         yield cur_q, cur_k
 
 
-def fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=None):
-    raise NotImplementedError("native backward not built yet")
+def attn_delta(out, dout, lse=None):
+    """-> delta (B,H,S) fp32 [, lse2 (B,H,S) log2-domain LSE with +inf for key-less rows]."""
+    dout = dout if dout.stride(-1) == 1 else dout.contiguous()
+    out = out if out.stride(-1) == 1 else out.contiguous()
+    r = ext().attn_delta(out, dout, None if lse is None else lse.contiguous())
+    return r[0] if lse is None else (r[0], r[1])
+
+
+def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=None, lse2=None,
+             dq=None, dk=None, dv=None, accumulate: bool = False, out_dtype=None, sm_limit: int = 0):
+    """Backward of one block: two tcgen05 passes (dQ, then dK/dV).  ``lse`` is the FINAL LSE of the
+    query rows (may cover more keys than this block: ring steps).  Returns (dq, dk, dv) in
+    ``out_dtype`` (default: input dtype; fp32 when ``accumulate``)."""
+    C = ext()
+    q, k, v, dout = _tma_ready(q), _tma_ready(k), _tma_ready(v), _tma_ready(dout)
+    if delta is None or lse2 is None:
+        delta, lse2 = attn_delta(out, dout, lse)
+    if out_dtype is None:
+        out_dtype = torch.float32 if accumulate else q.dtype
+    if dq is None:
+        assert not accumulate
+        dq = torch.empty(q.shape, dtype=out_dtype, device=q.device)
+        dk = torch.empty(k.shape, dtype=out_dtype, device=q.device)
+        dv = torch.empty(v.shape, dtype=out_dtype, device=q.device)
+    wl, wr = window_bounds(p)
+    alibi = p.alibi_slopes
+    if alibi is not None:
+        alibi = alibi.to(device=q.device, dtype=torch.float32).contiguous()
+    qs, ks = _common_stride(q_pos), _common_stride(k_pos)
+    qrows, krows = _rows(q_pos), _rows(k_pos)
+    for qchunk, kchunk in _chunk_by_group(qrows, krows):
+        xq = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in sorted(qchunk, key=lambda r: -r[2])]
+        yk = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in kchunk]
+        C.fmha_bwd_pass(False, q, dout, k, v, xq, yk, qs, ks, lse2, delta, dq, None, accumulate,
+                        float(p.softmax_scale), wl, wr, float(p.softcap), alibi, int(sm_limit))
+        xk = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in kchunk]
+        yq = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in qchunk]
+        # rows are keys, columns are queries: bounds on (qpos - kpos) are the mirrored window
+        C.fmha_bwd_pass(True, k, v, q, dout, xk, yq, ks, qs, lse2, delta, dk, dv, accumulate,
+                        float(p.softmax_scale), wr, wl, float(p.softcap), alibi, int(sm_limit))
+    return dq, dk, dv
 
 
 def merge_out_lse_(out_acc, lse_acc, block_out, block_lse) -> None:

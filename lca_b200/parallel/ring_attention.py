@@ -101,13 +101,14 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
     Lk = k.shape[1]
     qpos_of, kpos_of = _pos_builders(variant, R, Lq, Lk, cu_seqlens_q, cu_seqlens_k)
     q_pos = qpos_of(r)
+    lse2 = None
     if q.is_cuda and native.available() and dout.dtype in (torch.bfloat16, torch.float16):
-        delta = native.ext().attn_delta(out, dout.contiguous() if dout.stride(-1) != 1 else dout)
+        delta, lse2 = native.attn_delta(out, dout, lse)     # one fused pass: rowsum(dO o O) + log2-domain LSE
     else:
         delta = (dout.to(torch.float32) * out.to(torch.float32)).sum(-1).permute(0, 2, 1).contiguous()
     if R == 1:
         dm = _dropout_mask(dropout_seed, r, r, B, H, Lq, Lk, p.dropout_p, q.device)
-        dq, dk, dv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, kpos_of(0), p, engine, dm, delta)
+        dq, dk, dv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, kpos_of(0), p, engine, dm, delta, lse2)
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
     kv_comm, dkv_comm = RingComm(group), RingComm(group)
     k, v = k.contiguous(), v.contiguous()
@@ -122,7 +123,7 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
         bdk = bdv = None
         if block_is_visible(q_pos, k_pos, p):
             dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
-            bdq, bdk, bdv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta)
+            bdq, bdk, bdv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta, lse2)
             dq = bdq.to(torch.float32) if dq is None else dq.add_(bdq)
             bdk, bdv = bdk.to(torch.float32), bdv.to(torch.float32)
         if step == 0:

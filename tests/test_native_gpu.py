@@ -126,7 +126,12 @@ def test_util_kernels():
     assert torch.equal(C.permute_group(y, 4, False), x)
     o = torch.randn(2, 65, 3, 128, device="cuda", dtype=torch.bfloat16)
     do = torch.randn_like(o)
-    torch.testing.assert_close(C.attn_delta(o, do), (o.float() * do.float()).sum(-1).permute(0, 2, 1), atol=1e-3, rtol=1e-3)
+    lse_in = torch.randn(2, 3, 65, device="cuda")
+    lse_in[0, 0, :4] = float("-inf")
+    dl, l2 = C.attn_delta(o, do, lse_in)
+    torch.testing.assert_close(dl, (o.float() * do.float()).sum(-1).permute(0, 2, 1), atol=1e-3, rtol=1e-3)
+    assert torch.all(torch.isinf(l2[0, 0, :4]) & (l2[0, 0, :4] > 0))
+    torch.testing.assert_close(l2[1], lse_in[1] * 1.4426950408889634)
     cu = torch.tensor([0, 3, 10, 14], device="cuda", dtype=torch.int32)
     lse = torch.randn(3, 2, 7, device="cuda")
     flat = C.flatten_varlen_lse(lse, cu, 14)
@@ -153,3 +158,74 @@ def test_module_single_gpu_forward_backward():
     torch.testing.assert_close(out.float(), ref.float(), atol=2e-2, rtol=0)
     for a, b in ((q.grad, q2.grad), (k.grad, k2.grad), (v.grad, v2.grad)):
         torch.testing.assert_close(a.float(), b.float(), atol=5e-2, rtol=5e-2)
+
+
+BWD_CASES = [
+    (1, 128, 128, 1, 1, 128, {}),
+    (1, 256, 320, 2, 2, 128, {}),
+    (2, 333, 333, 3, 3, 128, dict(causal=True)),
+    (2, 200, 777, 4, 2, 64, {}),
+    (2, 1024, 1024, 8, 2, 128, dict(causal=True)),
+    (1, 1024, 1024, 2, 2, 128, dict(causal=True, window_size=(300, 0))),
+    (1, 1024, 1024, 2, 1, 64, dict(window_size=(100, 200))),
+    (1, 512, 512, 2, 2, 128, dict(causal=True, softcap=15.0)),
+    (1, 512, 512, 4, 4, 128, dict(causal=True, alibi=True)),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H,Hkv,D,kw", BWD_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_fmha_bwd_vs_oracle(B, Sq, Sk, H, Hkv, D, kw, dtype):
+    native = _native()
+    from lca_b200.ops.attention import AttnParams
+    from lca_b200.ops.ref_attention import attn_block_bwd_ref, attn_block_fwd_ref
+    from lca_b200.parallel.layout import Seg, pos_tensor
+    kw = dict(kw)
+    q, k, v = _mk(B, Sq, Sk, H, Hkv, D, dtype)
+    do = torch.randn_like(q)
+    slopes = torch.rand(H, device="cuda") * 0.5 if kw.pop("alibi", False) else None
+    p = AttnParams.make(q, None, kw.get("causal", False), kw.get("window_size", (-1, -1)), kw.get("softcap", 0.0), slopes)
+    qp, kp = (Seg(max(Sk - Sq, 0), Sq, 1),), (Seg(0, Sk, 1),)
+    out, lse = native.fmha_fwd(q, k, v, qp, kp, p)
+    dq, dk, dv = native.fmha_bwd(do, q, k, v, out, lse, qp, kp, p)
+    rq, rk, rv = attn_block_bwd_ref(do, q, k, v, out, lse, pos_tensor(qp, "cuda"), pos_tensor(kp, "cuda"), p.softmax_scale,
+                                    p.causal, p.window_size, p.softcap, slopes)
+    for name, a, b in (("dq", dq, rq), ("dk", dk, rk), ("dv", dv, rv)):
+        err = (a.float() - b).abs().max().item()
+        scale = b.abs().max().item() + 1e-6
+        assert err / scale < (2e-2 if dtype == torch.bfloat16 else 5e-3), f"{name}: err {err} vs scale {scale}"
+        assert torch.isfinite(a).all()
+
+
+def test_fmha_bwd_accumulate_fp32_and_ring_blocks():
+    """Ring-style accumulation: per-block backward with the GLOBAL lse, fp32 += into dq/dk/dv buffers."""
+    native = _native()
+    from lca_b200.ops.attention import AttnParams, merge_out_lse_
+    from lca_b200.ops.ref_attention import attention_ref, attn_block_bwd_ref
+    from lca_b200.parallel.layout import pos_tensor, ring_positions
+    R, S, H, D = 2, 1024, 2, 128
+    q, k, v = _mk(1, S, S, H, H, D)
+    do = torch.randn_like(q)
+    p = AttnParams.make(q, None, True)
+    out, lse = attention_ref(q, k, v, causal=True)
+    pos = torch.arange(S, device="cuda")
+    rq, rk, rv = attn_block_bwd_ref(do, q, k, v, out, lse, pos, pos, p.softmax_scale, True)
+    dq = torch.zeros(1, S, H, D, device="cuda")
+    dk, dv = torch.zeros_like(dq), torch.zeros_like(dq)
+    for r in range(R):
+        qpos = ring_positions("zigzag", r, R, S // R)
+        qi = pos_tensor(qpos, "cuda")
+        dq_r = torch.zeros(1, S // R, H, D, device="cuda")
+        for src in range(R):
+            kpos = ring_positions("zigzag", src, R, S // R)
+            ki = pos_tensor(kpos, "cuda")
+            dk_b = torch.zeros(1, S // R, H, D, device="cuda")
+            dv_b = torch.zeros_like(dk_b)
+            native.fmha_bwd(do[:, qi].contiguous(), q[:, qi].contiguous(), k[:, ki].contiguous(), v[:, ki].contiguous(),
+                            out[:, qi].contiguous(), lse[:, :, qi].contiguous(), qpos, kpos, p, dq=dq_r, dk=dk_b, dv=dv_b,
+                            accumulate=True)
+            dk[:, ki] += dk_b
+            dv[:, ki] += dv_b
+        dq[:, qi] = dq_r
+    for a, b in ((dq, rq), (dk, rk), (dv, rv)):
+        assert (a - b).abs().max().item() / (b.abs().max().item() + 1e-6) < 2e-2
