@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
 
   // ---- barriers
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp >= kMmaWarp) {
     setmaxnreg_dec<96>();
@@ -266,8 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         }
       }
     } else if (warp == kMmaWarp) {
-      // =========================================================== MMA issuer
-      if (lane == 0) {
+      // =========================================================== MMA issuer (whole warp, elected lane issues)
+      {
         constexpr uint32_t idesc_t = make_idesc_f16(kBf16 ? 1 : 0, BX, BY, 0, 0);
         constexpr uint32_t idesc_acc = make_idesc_f16(kBf16 ? 1 : 0, BX, kD, 0, 1);
         uint32_t xc = 0, yc = 0, pc[2] = {0, 0}, ac = 0;
@@ -401,6 +401,39 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
                                (p.wl >= 0 && xhi - it.ypos0 > p.wl) || (wk.nrows < BX);
         const float* st_l2 = stat + st * 2 * BY;
         const float* st_dl = st_l2 + BY;
+        float mul = p.scale_log2;
+        if (!plain || need_mask) {
+          // general pre-pass (rolled, keeps the hot loop small): rewrite T0 as masked log2-domain logits
+          // and T1 as dl + (T1 - dl) * softcap'(s), so the common loop below needs no special cases.
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t t0[32], t1[32];
+            tmem_ld32(tT0 + half * 32, t0);
+            tmem_ld32(tT1 + half * 32, t1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int col = half * 32 + i;
+              const float dl = kIsDKV ? st_dl[col] : delta_r;
+              float x = __uint_as_float(t0[i]) * p.scale;
+              float extra = 1.f;
+              if (p.softcap > 0.f) {
+                const float th = tanh_approx(x / p.softcap);
+                x = p.softcap * th;
+                extra = 1.f - th * th;
+              }
+              const int rel = it.ypos0 + col * p.y_pos_stride - xpos;
+              if (p.alibi) x -= slope * fabsf(static_cast<float>(rel));
+              const bool masked = (col >= it.nvalid) || !row_ok || (p.wr >= 0 && rel > p.wr) || (p.wl >= 0 && -rel > p.wl);
+              t0[i] = __float_as_uint(masked ? -INFINITY : x * 1.4426950408889634f);
+              t1[i] = __float_as_uint(masked ? dl : fmaf(__uint_as_float(t1[i]) - dl, extra, dl));
+            }
+            tmem_st32(tT0 + half * 32, t0);
+            tmem_st32(tT1 + half * 32, t1);
+          }
+          tmem_wait_st();
+          mul = 1.f;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t t0[32], t1[32];
@@ -409,35 +442,29 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           tmem_wait_ld();
           uint32_t pp[16], ds[16];
 #pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float pv[2], dv[2];
+          for (int c = 0; c < 32; c += 4) {
+            float l2v[4], dlv[4];
+            if constexpr (kIsDKV) {
+              const float4 a4 = *reinterpret_cast<const float4*>(st_l2 + half * 32 + c);
+              const float4 b4 = *reinterpret_cast<const float4*>(st_dl + half * 32 + c);
+              l2v[0] = a4.x; l2v[1] = a4.y; l2v[2] = a4.z; l2v[3] = a4.w;
+              dlv[0] = b4.x; dlv[1] = b4.y; dlv[2] = b4.z; dlv[3] = b4.w;
+            } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int col = half * 32 + c + e;
-              const float l2 = kIsDKV ? st_l2[col] : lse2_r;
-              const float dl = kIsDKV ? st_dl[col] : delta_r;
-              const float s_raw = __uint_as_float(t0[c + e]);
-              float pe, extra = 1.f;
-              bool masked = false;
-              if (plain && !need_mask) {
-                pe = ex2(fmaf(s_raw, p.scale_log2, -l2));
-              } else {
-                float x = s_raw * p.scale;
-                if (p.softcap > 0.f) {
-                  const float th = tanh_approx(x / p.softcap);
-                  x = p.softcap * th;
-                  extra = 1.f - th * th;
-                }
-                const int rel = it.ypos0 + col * p.y_pos_stride - xpos;
-                if (p.alibi) x -= slope * fabsf(static_cast<float>(rel));
-                masked = (col >= it.nvalid) || !row_ok || (p.wr >= 0 && rel > p.wr) || (p.wl >= 0 && -rel > p.wl);
-                pe = masked ? 0.f : ex2(fmaf(x, 1.4426950408889634f, -l2));
-              }
-              pv[e] = pe;
-              dv[e] = masked ? 0.f : pe * (__uint_as_float(t1[c + e]) - dl) * extra;   // never 0 * garbage
+              for (int e = 0; e < 4; ++e) { l2v[e] = lse2_r; dlv[e] = delta_r; }
             }
-            pp[c >> 1] = pack2<kBf16>(pv[0], pv[1]);
-            ds[c >> 1] = pack2<kBf16>(dv[0], dv[1]);
+            float pv[4], dv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              pv[e] = ex2(fmaf(__uint_as_float(t0[c + e]), mul, -l2v[e]));
+              dv[e] = pv[e] * (__uint_as_float(t1[c + e]) - dlv[e]);
+            }
+            if constexpr (kIsDKV) {
+              pp[(c >> 1)] = pack2<kBf16>(pv[0], pv[1]);
+              pp[(c >> 1) + 1] = pack2<kBf16>(pv[2], pv[3]);
+            }
+            ds[(c >> 1)] = pack2<kBf16>(dv[0], dv[1]);
+            ds[(c >> 1) + 1] = pack2<kBf16>(dv[2], dv[3]);
           }
           if constexpr (kIsDKV) tmem_st16(tT0 + half * 16, pp);
           tmem_st16(tT1 + half * 16, ds);

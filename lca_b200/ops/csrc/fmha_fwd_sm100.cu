@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
 
   // ---- barrier carve-up
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int hk_div = p.H / p.Hkv;
 
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       }
     }
    } else if (warp == kMmaWarp) {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
+    // =========================================================== MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc_qk = make_idesc_f16(kBf16 ? 1 : 0, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(kBf16 ? 1 : 0, BM, kD, 0, 1);
       uint32_t qc[2] = {0, 0}, pc[2] = {0, 0};
