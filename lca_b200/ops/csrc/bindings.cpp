@@ -89,11 +89,11 @@ static int num_sms() {
 // ------------------------------------------------------------------------------------ fmha fwd
 // qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr, group}
 // ksegs[i] = {row0, nrows, pos0, flag, group}
-void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
               const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
               int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
               double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
-              int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit) {
+              int64_t flags_ptr, int64_t flag_epoch) {
   TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda(), "q/k/v must be CUDA tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
   TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(), "dtype mismatch");
@@ -105,9 +105,6 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
   TORCH_CHECK(k.size(0) == B && v.size(0) == B && v.size(1) == k.size(1), "bad k/v batch/seq");
   TORCH_CHECK(!qsegs.empty() && qsegs.size() <= kMaxSeg && !ksegs.empty() && ksegs.size() <= kMaxSeg, "segment count");
   TORCH_CHECK(scale > 0, "softmax_scale must be positive");
-  c10::cuda::CUDAGuard guard(q.device());
-
-  FwdParams p;
   std::memset(&p, 0, sizeof(p));
   make_tmap(&p.tm_q, q, "q");
   make_tmap(&p.tm_k, k, "k");
@@ -171,9 +168,76 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
   TORCH_CHECK(lse.size(0) == B && lse.size(1) == H && lse.size(2) >= q.size(1), "lse shape");
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
+}
+
+void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+              const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
+              int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
+              double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
+              int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit) {
+  c10::cuda::CUDAGuard guard(q.device());
+  FwdParams p;
+  fill_fwd_params(p, q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap,
+                  alibi, flags_ptr, flag_epoch);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
-  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(D), q.scalar_type() == at::kBFloat16, sms,
+  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
+                              at::cuda::getCurrentCUDAStream()));
+}
+
+// Fused USP forward: the same kernel with `n_comm` communication CTAs that push this rank's q/k/v shards
+// (`uq`, `uk`, `uv`: user tensors (B, S/P, H|Hkv, D)) into the peers' staging buffers while the compute CTAs
+// consume `q`, `k`, `v` (= views of MY staging buffers, or the user q when U == 1) segment by segment.
+// mesh = {P, U, R, u, r, rows, push_q, n_comm};  offs = {off_q, off_k, off_v, stage_q_rows, stage_kv_rows}
+void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& uq, const at::Tensor& uk,
+             const at::Tensor& uv, const std::vector<std::vector<int64_t>>& qsegs,
+             const std::vector<std::vector<int64_t>>& ksegs, int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out,
+             int64_t o_head_off, at::Tensor& lse, double scale, int64_t wl, int64_t wr, double softcap,
+             const c10::optional<at::Tensor>& alibi, const std::vector<int64_t>& mesh, const std::vector<int64_t>& offs,
+             const std::vector<int64_t>& peer_slabs, const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch,
+             int64_t o_target) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(mesh.size() == 8 && offs.size() == 5, "mesh/offs arity");
+  const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
+  TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
+              static_cast<int>(peer_sigs.size()) == P, "peer tables");
+  const int n_comm = static_cast<int>(mesh[7]);
+  TORCH_CHECK(n_comm >= 1 && n_comm <= 64, "n_comm");
+  FwdParams p;
+  fill_fwd_params(p, q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap,
+                  alibi, my_sig, epoch * n_comm);
+  CommParams& c = p.comm;
+  c.n_comm = n_comm;
+  c.P = P; c.U = U; c.R = R;
+  c.u = static_cast<int>(mesh[3]); c.r = static_cast<int>(mesh[4]);
+  c.rows = static_cast<int>(mesh[5]);
+  c.push_q = static_cast<int>(mesh[6]);
+  c.B = static_cast<int>(uq.size(0)); c.H = static_cast<int>(uq.size(2)); c.Hkv = static_cast<int>(uk.size(2));
+  c.D = static_cast<int>(uq.size(3));
+  TORCH_CHECK(uq.size(1) == c.rows && uk.size(1) == c.rows && uv.size(1) == c.rows, "local shard rows");
+  TORCH_CHECK(c.H % U == 0, "query heads must be divisible by the Ulysses degree");
+  TORCH_CHECK(c.Hkv % U == 0 || U % c.Hkv == 0, "kv heads must divide or be divisible by the Ulysses degree");
+  c.Hl = c.H / U;
+  c.Hkvl = c.Hkv >= U ? c.Hkv / U : 1;
+  for (const at::Tensor* t : {&uq, &uk, &uv}) {
+    TORCH_CHECK(t->is_cuda() && t->stride(3) == 1 && t->stride(2) == t->size(3), "q/k/v shards need dense (head, dim) axes");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0 && t->stride(1) % 8 == 0 && t->stride(0) % 8 == 0,
+                "q/k/v shards must be 16-byte aligned");
+  }
+  c.q = uq.data_ptr(); c.k = uk.data_ptr(); c.v = uv.data_ptr();
+  c.q_sb = uq.stride(0); c.q_ss = uq.stride(1);
+  c.k_sb = uk.stride(0); c.k_ss = uk.stride(1);
+  c.v_sb = uv.stride(0); c.v_ss = uv.stride(1);
+  for (int i = 0; i < P; ++i) {
+    c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
+    c.peer_sig[i] = reinterpret_cast<unsigned int*>(peer_sigs[i]);
+  }
+  c.my_sig = reinterpret_cast<unsigned int*>(my_sig);
+  c.off_q = offs[0]; c.off_k = offs[1]; c.off_v = offs[2];
+  c.stage_q_rows = offs[3]; c.stage_kv_rows = offs[4];
+  c.epoch = static_cast<unsigned int>(epoch);
+  c.o_target = static_cast<unsigned int>(o_target);
+  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }
 
@@ -369,6 +433,7 @@ std::vector<at::Tensor> attn_delta(const at::Tensor& out, const at::Tensor& dout
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lca_b200 sm_100a kernels";
   m.def("fmha_fwd", &lca::fmha_fwd, "tcgen05 flash-attention forward (segments + global positions)");
+  m.def("usp_fwd", &lca::usp_fwd, "fused USP forward: NVLink push CTAs + tcgen05 attention CTAs in one kernel");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
   m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");
   m.def("finalize_out", &lca::finalize_out, "fp32 accumulator -> 16-bit output");

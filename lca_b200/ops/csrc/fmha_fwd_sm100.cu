@@ -77,9 +77,10 @@ __device__ __forceinline__ bool decode_work(const FwdParams& p, int w, Work& wk)
 
 // static "snake" schedule: round k visits work k*G + c on even rounds and k*G + (G-1-c) on odd
 // rounds, which cancels the cost gradient of the heaviest-first ordering across CTAs.
-__device__ __forceinline__ int sched_work(int round) {
-  const int G = gridDim.x;
-  const int c = (round & 1) ? (G - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
+__device__ __forceinline__ int sched_work(int round, int n_comm) {
+  const int G = static_cast<int>(gridDim.x) - n_comm;          // compute CTAs
+  const int me = static_cast<int>(blockIdx.x) - n_comm;
+  const int c = (round & 1) ? (G - 1 - me) : me;
   return round * G + c;
 }
 
@@ -140,6 +141,100 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Communication CTAs of the fused USP kernel.
+// For every destination sp-rank d (self first, then rotated so NVSwitch ports are evenly loaded):
+//   wait until d has entered this call (ready-to-receive flag), copy my K/V head-slice for d -- and my
+//   Q head-slice if d is in my Ulysses group -- into d's staging with 16-byte st.global over NVLink,
+//   then fence.sys + red.release.sys on d's arrival counters.  The compute CTAs of d poll those
+//   counters with ld.acquire.sys right before the TMA loads of the matching segment.
+struct CopyMsg {
+  const unsigned char* src;
+  unsigned char* dst;
+  long long src_sb, src_ss, dst_sb, dst_ss;   // bytes
+  int nrows, row_vecs;                        // rows per batch, 16-byte vectors per row
+};
+
+__device__ __forceinline__ void comm_copy(const CopyMsg& m, int B, int tid, int nthreads) {
+  const long long total = static_cast<long long>(B) * m.nrows * m.row_vecs;
+  constexpr int UNR = 4;
+  for (long long base = static_cast<long long>(tid) * UNR; base < total; base += static_cast<long long>(nthreads) * UNR) {
+    uint4 val[UNR];
+    long long doff[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const long long i = base + j;
+      doff[j] = -1;
+      if (i < total) {
+        const int c = static_cast<int>(i % m.row_vecs);
+        const long long br = i / m.row_vecs;
+        const int row = static_cast<int>(br % m.nrows);
+        const int b = static_cast<int>(br / m.nrows);
+        val[j] = *reinterpret_cast<const uint4*>(m.src + b * m.src_sb + row * m.src_ss + c * 16);
+        doff[j] = b * m.dst_sb + row * m.dst_ss + c * 16;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j)
+      if (doff[j] >= 0) *reinterpret_cast<uint4*>(m.dst + doff[j]) = val[j];
+  }
+}
+
+__device__ void comm_cta(const FwdParams& p) {
+  const CommParams& c = p.comm;
+  const int tid = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int nthreads = c.n_comm * blockDim.x;
+  const int me = c.r * c.U + c.u;
+  const int esz = 2;
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < c.P)      // tell every peer my staging is free for this call
+    st_release_sys(c.peer_sig[threadIdx.x] + kSigRTR + me, c.epoch);
+  const long long row_off_kv = static_cast<long long>(c.r) * c.U * c.rows + static_cast<long long>(c.u) * c.rows;
+  const long long row_off_q = static_cast<long long>(c.u) * c.rows;
+  for (int i = 0; i < c.P; ++i) {
+    const int d = (me + i) % c.P;
+    const int du = d % c.U, dr = d / c.U;
+    if (threadIdx.x == 0) {
+      while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigRTR + d) - c.epoch) < 0) __nanosleep(32);
+    }
+    __syncthreads();
+    // K and V head-slice of destination du: kv head(s) [h0, h0 + Hkvl)
+    const int h0 = (c.Hkv >= c.U) ? du * c.Hkvl : (du * c.Hkv) / c.U;
+    CopyMsg m;
+    m.nrows = c.rows;
+    m.row_vecs = c.Hkvl * c.D * esz / 16;
+    m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
+    m.dst_sb = c.stage_kv_rows * m.dst_ss;
+    m.src = static_cast<const unsigned char*>(c.k) + static_cast<long long>(h0) * c.D * esz;
+    m.src_sb = c.k_sb * esz; m.src_ss = c.k_ss * esz;
+    m.dst = c.peer_slab[d] + c.off_k + row_off_kv * m.dst_ss;
+    comm_copy(m, c.B, tid, nthreads);
+    m.src = static_cast<const unsigned char*>(c.v) + static_cast<long long>(h0) * c.D * esz;
+    m.src_sb = c.v_sb * esz; m.src_ss = c.v_ss * esz;
+    m.dst = c.peer_slab[d] + c.off_v + row_off_kv * m.dst_ss;
+    comm_copy(m, c.B, tid, nthreads);
+    const bool send_q = c.push_q && dr == c.r;
+    if (send_q) {
+      m.row_vecs = c.Hl * c.D * esz / 16;
+      m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
+      m.dst_sb = c.stage_q_rows * m.dst_ss;
+      m.src = static_cast<const unsigned char*>(c.q) + static_cast<long long>(du) * c.Hl * c.D * esz;
+      m.src_sb = c.q_sb * esz; m.src_ss = c.q_ss * esz;
+      m.dst = c.peer_slab[d] + c.off_q + row_off_q * m.dst_ss;
+      comm_copy(m, c.B, tid, nthreads);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
+      if (send_q) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
+    }
+  }
+  // my output buffer is complete once every compute rank has scattered its O tiles into it
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.o_target != 0) {
+    while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigODone) - c.o_target) < 0) __nanosleep(64);
+  }
+}
+
 struct Bars {
   uint32_t q_full[2], q_empty[2], s_full[2], p_full[2], o_full[2];
   uint32_t kv_full, kv_empty;   // base addresses of STAGES-long arrays
@@ -150,6 +245,10 @@ struct Bars {
 template <int kD, bool kBf16>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
+  if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
+    comm_cta(p);
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
@@ -208,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       int q_flag_ok = -1, k_flag_ok = -1;
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round), wk)) break;
+        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
         const int qf = p.qseg[wk.qseg].flag;
         if (qf >= 0 && qf != q_flag_ok) { wait_flag(p, qf); q_flag_ok = qf; }
         for (int t = 0; t < wk.ntile; ++t) {
@@ -269,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       };
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round), wk)) break;
+        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
         const int nt = wk.ntile;
         TileIter it;
         it.init(p, wk);
@@ -336,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
-      if (!decode_work(p, sched_work(round), wk)) break;
+      if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
       if (t >= wk.ntile) continue;
       const int qpos = wk.pos0 + (t * BM + row) * p.q_pos_stride;
       const int qlo_t = wk.pos0 + t * BM * p.q_pos_stride;
@@ -520,8 +619,10 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int grid = p.total_work < num_sms ? p.total_work : num_sms;
+  const int avail = num_sms - p.comm.n_comm;
+  int grid = p.total_work < avail ? p.total_work : avail;
   if (grid < 1) grid = 1;
+  grid += p.comm.n_comm;       // comm CTAs first; all CTAs are co-resident (1 CTA/SM, grid <= #SMs)
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }

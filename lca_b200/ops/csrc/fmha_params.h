@@ -31,6 +31,36 @@ struct KSegD {
   int group;
 };
 
+constexpr int kMaxPeers = 16;
+
+// Signal-pad layout (uint32 slots) of every rank's symmetric slab.  All counters are monotonic
+// across calls ("epochs"), so nothing is ever reset while peers may still be polling.
+constexpr int kSigKV = 0;        // [kSigKV + src]   : K/V shard of sp-rank `src` has landed   (+n_comm per call)
+constexpr int kSigQ = 16;        // [kSigQ + src_u]  : Q shard of Ulysses-rank `src_u` landed  (+n_comm per call)
+constexpr int kSigRTR = 32;      // [kSigRTR + dst]  : `dst` entered call `epoch` (its staging may be overwritten)
+constexpr int kSigODone = 48;    // output tiles written into my out buffer by all compute ranks (cumulative)
+constexpr int kSigSlots = 64;
+
+// The communication half of the fused USP kernel: CTAs [0, n_comm) push this rank's Q/K/V
+// head-slices into the peers' staging buffers with plain st.global over NVLink.
+struct CommParams {
+  int n_comm;                        // 0: no comm role (plain single-device attention)
+  int P, U, R, u, r;                 // mesh: sp size, degrees, my coordinates; sp-rank = r*U + u
+  int rows;                          // local tokens S/P
+  int B, H, Hkv, D;
+  int Hl, Hkvl;                      // heads per destination (Hkvl = max(1, Hkv/U))
+  int push_q;                        // 0 when U == 1 (Q is read in place)
+  const void *q, *k, *v;             // my shards (B, rows, H|Hkv, D), last two dims dense
+  long long q_sb, q_ss, k_sb, k_ss, v_sb, v_ss;   // element strides (batch, row)
+  unsigned char* peer_slab[kMaxPeers];   // mapped base of every sp-rank's slab (index = sp-rank)
+  unsigned int* peer_sig[kMaxPeers];     // mapped signal pad of every sp-rank
+  unsigned int* my_sig;
+  long long off_q, off_k, off_v;     // byte offsets of the staging tensors inside a slab
+  long long stage_q_rows, stage_kv_rows;   // rows of the staging tensors (S/R and S)
+  unsigned int epoch;                // 1-based call counter
+  unsigned int o_target;             // value kSigODone must reach before this rank's kernel may exit (0: skip)
+};
+
 struct FwdParams {
   CUtensorMap tm_q, tm_k, tm_v;       // 4-D (D, H, S, B) bf16/fp16, box (64, 1, 128, 1), SWIZZLE_128B
   int n_qseg, n_kseg;
@@ -51,6 +81,7 @@ struct FwdParams {
   int64_t lse_sb, lse_sh;
   const uint32_t* flags;              // arrival flags written by peers (fused paths)
   uint32_t flag_epoch;
+  CommParams comm;
 };
 
 // ---- backward -----------------------------------------------------------------------------------

@@ -1,0 +1,311 @@
+"""Fused NVLink USP engine: Ulysses head shuffle + ring K/V exchange + attention in ONE kernel per rank.
+
+What replaces what (reference call sites in parentheses):
+
+* 3x ``all_to_all_single`` + 6 staging copies before attention (``hybrid/attn_layer.py:111-119``,
+  ``comm/all_to_all.py:45-65``)  ->  communication CTAs of the attention kernel push each head-slice
+  straight from the caller's q/k/v tensors into the consumer rank's staging buffer with 16-byte
+  ``st.global`` over NVLink (no NCCL, no intermediate copy, strided packed-QKV views accepted).
+* ``R-1`` rounds of ``batch_isend_irecv(K,V)`` + ``R`` flash-attn launches + ``R`` LSE-merge launches
+  (``ring/zigzag_ring_flash_attn.py:45-72``)  ->  the same kernel's compute CTAs walk ALL K/V
+  segments (own shard first, then peers' in arrival order) with one online softmax carried in
+  registers/TMEM; segments are gated by ``ld.acquire.sys`` arrival counters, so the transfer of
+  shard ``j+1`` overlaps the tcgen05 math on shard ``j`` tile by tile.  NVSwitch makes every peer
+  one hop away, so the "ring" is only a schedule, not a topology.
+* output ``all_to_all_single`` + 2 copies (``hybrid/attn_layer.py:156-158``)  ->  the epilogue of every
+  128-row O tile stores it into the token owner's output buffer over NVLink and bumps the owner's
+  completion counter with ``red.release.sys``.
+
+Memory: one symmetric slab per rank (cudaMalloc + CUDA IPC, handles exchanged once through the
+process group's store), laid out as ``[signal pad | Q stage | K stage | V stage | out]``.
+All counters are monotonic "epochs" -- nothing is reset between calls, so there is no barrier
+kernel on the hot path; the only cross-rank handshake is a ready-to-receive flag written at the
+top of each call.
+
+Backward currently reuses the collective path (NCCL all-to-all + P2P ring around the tcgen05
+backward kernels); the saved LSE is produced in exactly the layout that path expects.
+"""
+from __future__ import annotations
+
+import os
+import socket
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import native
+from ..ops.attention import AttnParams
+from .layout import Seg, canonical_variant, ring_positions, slice_pos
+
+SIG_BYTES = 4096
+SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE = 0, 16, 32, 48
+MAX_PEERS = 16
+_ALIGN = 1024
+
+
+def _align(x: int) -> int:
+    return (x + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class _Slab:
+    """This rank's symmetric slab + mapped views of every peer's slab."""
+
+    def __init__(self, nbytes: int, group, device: torch.device):
+        C = native.ext()
+        self.nbytes = nbytes
+        self.device = device
+        self.ptr = C.symm_alloc(nbytes, device.index)
+        handle = C.symm_export(self.ptr)
+        world = dist.get_world_size(group)
+        handles: List[Optional[bytes]] = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        me = dist.get_rank(group)
+        self.peer_ptrs = [self.ptr if i == me else C.symm_import(handles[i], device.index) for i in range(world)]
+        self._me = me
+
+    def tensor(self, offset: int, shape, dtype) -> torch.Tensor:
+        return native.ext().symm_tensor(self.ptr + offset, list(shape), dtype, self.device.index)
+
+    def close(self):
+        C = native.ext()
+        for i, p in enumerate(self.peer_ptrs):
+            if i != self._me:
+                C.symm_unmap(p)
+        C.symm_free(self.ptr)
+
+
+class FusedUSPEngine:
+    def __init__(self, sp_group, U: int, R: int, u: int, r: int, device: torch.device):
+        self.group, self.U, self.R, self.u, self.r = sp_group, U, R, u, r
+        self.P = U * R
+        self.me = r * U + u                     # index inside the sp group (ulysses-low ordering)
+        self.device = device
+        self.slab: Optional[_Slab] = None
+        self.sig: Optional[_Slab] = None
+        self.key = None
+        self.epoch = 0
+        self.o_total = 0
+        self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "8"))
+        # the signal pad lives in its own small slab so that growing the data slab never resets counters
+        self.sig = _Slab(SIG_BYTES, sp_group, device)
+
+    # ------------------------------------------------------------------------------ workspace
+    def _ensure(self, B, rows, H, Hkv, D, esz):
+        U, R = self.U, self.R
+        Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
+        key = (B, rows, H, Hkv, D, esz)
+        if key == self.key:
+            return
+        sq = B * (U * rows) * Hl * D * esz if U > 1 else 0
+        skv = B * (self.P * rows) * Hkvl * D * esz
+        so = B * rows * H * D * esz if U > 1 else 0
+        self.off_q = 0
+        self.off_k = _align(self.off_q + sq)
+        self.off_v = _align(self.off_k + skv)
+        self.off_o = _align(self.off_v + skv)
+        total = _align(self.off_o + so) + _ALIGN
+        if self.slab is None or self.slab.nbytes < total:
+            if self.slab is not None:
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)      # nobody may still be writing into the old slab
+                self.slab.close()
+            self.slab = _Slab(total, self.group, self.device)
+        self.key = key
+
+    # ------------------------------------------------------------------------------ forward
+    def forward(self, q, k, v, variant: str, p: AttnParams):
+        """q (B, S/P, H, D), k/v (B, S/P, Hkv, D) local shards -> out (B, S/P, H, D), lse (B, H/U, S/R)."""
+        C = native.ext()
+        U, R, u, r, P = self.U, self.R, self.u, self.r, self.P
+        B, rows, H, D = q.shape
+        Hkv = k.shape[2]
+        esz = q.element_size()
+        if H % U:
+            raise ValueError(f"query heads ({H}) must be divisible by the Ulysses degree ({U})")
+        if not (Hkv % U == 0 or U % Hkv == 0):
+            raise ValueError(f"kv heads ({Hkv}) must divide or be divisible by the Ulysses degree ({U})")
+        Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
+        q, k, v = (_dense_heads(t) for t in (q, k, v))
+        self._ensure(B, rows, H, Hkv, D, esz)
+        slab = self.slab
+        Sr = U * rows                            # tokens per ring rank after the Ulysses gather
+        self.epoch += 1
+        push_q = 1 if U > 1 else 0
+        kst = slab.tensor(self.off_k, (B, P * rows, Hkvl, D), q.dtype)
+        vst = slab.tensor(self.off_v, (B, P * rows, Hkvl, D), q.dtype)
+        if push_q:
+            qst = slab.tensor(self.off_q, (B, Sr, Hl, D), q.dtype)
+            out_local = slab.tensor(self.off_o, (B, rows, H, D), q.dtype)
+        else:
+            qst = q
+            out_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B, Hl, Sr), dtype=torch.float32, device=q.device)
+
+        # ---- segments (positions of the gathered sequence of ring rank r, split by source shard)
+        qsegs = []
+        n_my_tiles = 0
+        my_ring_pos = ring_positions(variant, r, R, Sr)
+        for su in range(U):
+            owner = r * U + su
+            for s, row0 in _slices_with_rows(my_ring_pos, su * rows, (su + 1) * rows):
+                if push_q:
+                    o_base = slab.peer_ptrs[owner] + self.off_o
+                    o_sig = self.sig.peer_ptrs[owner] + 4 * SIG_ODONE
+                    flag = SIG_Q + su
+                else:
+                    o_base, o_sig, flag = 0, 0, -1
+                qsegs.append([row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0])
+                if su == u:
+                    n_my_tiles += (s.count + 127) // 128
+        qsegs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
+        ksegs = []
+        order = [(r - i) % R for i in range(R)]  # own ring block first, then in "ring step" order
+        for sr in order:
+            pos = ring_positions(variant, sr, R, Sr)
+            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
+            for su in us:
+                src = sr * U + su
+                for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
+                    ksegs.append([sr * Sr + row0, s.count, s.start, SIG_KV + src, 0])
+        qstride = R if canonical_variant(variant) == "stripe" else 1
+        wl, wr = native.window_bounds(p)
+        alibi = p.alibi_slopes
+        if alibi is not None:
+            alibi = alibi.to(device=q.device, dtype=torch.float32)[..., u * Hl:(u + 1) * Hl].contiguous()
+        if push_q:
+            self.o_total += U * B * Hl * n_my_tiles
+            o_target = self.o_total & 0xFFFFFFFF
+        else:
+            o_target = 0
+        C.usp_fwd(qst, kst, vst, q, k, v, qsegs, ksegs, qstride, qstride, out_local, u * Hl, lse,
+                  float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
+                  [P, U, R, u, r, rows, push_q, self.n_comm],
+                  [self.off_q, self.off_k, self.off_v, Sr, P * rows],
+                  slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
+        out = out_local.clone() if push_q else out_local   # the symmetric out buffer is reused next call
+        return out, lse
+
+    # ------------------------------------------------------------------------------ autograd entry
+    def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic):
+        p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, 0.0, deterministic)
+        return _FusedAttnFunc.apply(q, k, v, self, canonical_variant(variant), p)
+
+
+def _dense_heads(t: torch.Tensor) -> torch.Tensor:
+    ok = (t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) % 8 == 0 and t.stride(0) % 8 == 0
+          and t.data_ptr() % 16 == 0)
+    return t if ok else t.contiguous()
+
+
+def _slices_with_rows(spec, begin: int, end: int):
+    """Position segments of local rows [begin, end) together with their first row index."""
+    out, off = [], 0
+    for s in spec:
+        lo, hi = max(begin, off), min(end, off + s.count)
+        if hi > lo:
+            out.append((Seg(s.start + (lo - off) * s.stride, hi - lo, s.stride, s.group), lo))
+        off += s.count
+    return out
+
+
+class _FusedAttnFunc(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams):
+        out, lse = eng.forward(q, k, v, variant, p)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.eng, ctx.variant, ctx.p = eng, variant, p
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        """Collective backward (NCCL a2a + ring P2P around the tcgen05 backward kernels)."""
+        from ..globals import PROCESS_GROUP
+        from .all_to_all import all_to_all_4D
+        from .ring_attention import ring_attn_backward
+        q, k, v, out, lse = ctx.saved_tensors
+        eng, p = ctx.eng, ctx.p
+        ug, rg = eng.ulysses_pg, eng.ring_pg
+        if eng.U > 1 and k.shape[2] % eng.U:
+            raise NotImplementedError("backward with kv_heads < ulysses degree needs the fused backward (round 2)")
+        a2a = (lambda t: all_to_all_4D(t.contiguous(), 2, 1, group=ug)) if eng.U > 1 else (lambda t: t)
+        alibi = p.alibi_slopes
+        if alibi is not None and eng.U > 1:
+            hl = q.shape[2] // eng.U
+            alibi = alibi[..., eng.u * hl:(eng.u + 1) * hl].contiguous()
+        from dataclasses import replace
+        pl = replace(p, alibi_slopes=alibi)
+        dq, dk, dv = ring_attn_backward(rg, a2a(dout), a2a(q), a2a(k), a2a(v), a2a(out), lse, ctx.variant, pl)
+        back = (lambda t: all_to_all_4D(t.contiguous(), 1, 2, group=ug)) if eng.U > 1 else (lambda t: t)
+        return back(dq), back(dk), back(dv), None, None, None
+
+
+# ---------------------------------------------------------------------------------- factories
+_ENGINES = {}
+
+
+def _same_node_p2p(group, device) -> bool:
+    world = dist.get_world_size(group)
+    info = [None] * world
+    dist.all_gather_object(info, (socket.gethostname(), device.index), group=group)
+    if len({h for h, _ in info}) != 1:
+        return False
+    C = native.ext()
+    return all(d == device.index or C.can_access_peer(device.index, d) for _, d in info)
+
+
+def _supported_input(q) -> bool:
+    return (q.is_cuda and native.available() and q.dtype in (torch.bfloat16, torch.float16)
+            and q.shape[-1] in native.SUPPORTED_HEAD_DIMS)
+
+
+def engine_for_mesh(pgs, q, strict: bool = False):
+    """Engine for the global U x R mesh set by set_seq_parallel_pg (collective on first call)."""
+    mesh = pgs.mesh
+    if mesh is None or mesh.sp_degree == 1 or pgs.SP_PG is None:
+        return None
+    if not _supported_input(q) or mesh.sp_degree > MAX_PEERS:
+        if strict:
+            raise RuntimeError("fused backend unavailable for this input/mesh")
+        return None
+    key = ("mesh", id(pgs.SP_PG), q.device.index)
+    if key not in _ENGINES:
+        if not mesh.use_ulysses_low:
+            if strict:
+                raise RuntimeError("fused backend requires use_ulysses_low=True")
+            _ENGINES[key] = None
+        elif not _same_node_p2p(pgs.SP_PG, q.device):
+            if strict:
+                raise RuntimeError("fused backend needs all SP ranks on one node with P2P access")
+            _ENGINES[key] = None
+        else:
+            eng = FusedUSPEngine(pgs.SP_PG, mesh.ulysses_degree, mesh.ring_degree, mesh.ulysses_rank, mesh.ring_rank,
+                                 q.device)
+            eng.ulysses_pg, eng.ring_pg = pgs.ULYSSES_PG, pgs.RING_PG
+            _ENGINES[key] = eng
+    return _ENGINES[key]
+
+
+def engine_for_ulysses_group(group, q, strict: bool = False):
+    """Engine for a bare Ulysses group (UlyssesAttention(sequence_process_group=...))."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    world = dist.get_world_size(group)
+    if world == 1:
+        return None
+    if not _supported_input(q) or world > MAX_PEERS:
+        if strict:
+            raise RuntimeError("fused backend unavailable for this input/group")
+        return None
+    key = ("ulysses", id(group), q.device.index)
+    if key not in _ENGINES:
+        g = group if group is not None else dist.group.WORLD
+        if not _same_node_p2p(g, q.device):
+            if strict:
+                raise RuntimeError("fused backend needs all ranks on one node with P2P access")
+            _ENGINES[key] = None
+        else:
+            eng = FusedUSPEngine(g, world, 1, dist.get_rank(g), 0, q.device)
+            eng.ulysses_pg, eng.ring_pg = g, None
+            _ENGINES[key] = eng
+    return _ENGINES[key]
