@@ -109,7 +109,13 @@ def set_seq_parallel_pg(
     PROCESS_GROUP.initialized = True
 
 
+def _is_self_group(group) -> bool:
+    return type(group).__name__ == "_SelfGroupType"
+
+
 def group_size(group) -> int:
+    if _is_self_group(group):
+        return 1
     if group is None:
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size()
@@ -118,6 +124,8 @@ def group_size(group) -> int:
 
 
 def group_rank(group) -> int:
+    if _is_self_group(group):
+        return 0
     if group is None:
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank()

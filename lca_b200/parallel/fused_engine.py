@@ -209,6 +209,13 @@ def _slices_with_rows(spec, begin: int, end: int):
     return out
 
 
+class _SelfGroupType:
+    """Sentinel process group of size 1 (see globals.group_size / group_rank)."""
+
+
+_SelfGroup = _SelfGroupType()
+
+
 class _FusedAttnFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams):
@@ -235,6 +242,8 @@ class _FusedAttnFunc(torch.autograd.Function):
             alibi = alibi[..., eng.u * hl:(eng.u + 1) * hl].contiguous()
         from dataclasses import replace
         pl = replace(p, alibi_slopes=alibi)
+        if eng.R == 1:      # no ring dimension: `None` would mean the WORLD group to the ring loop
+            rg = _SelfGroup
         dq, dk, dv = ring_attn_backward(rg, a2a(dout), a2a(q), a2a(k), a2a(v), a2a(out), lse, ctx.variant, pl)
         back = (lambda t: all_to_all_4D(t.contiguous(), 1, 2, group=ug)) if eng.U > 1 else (lambda t: t)
         return back(dq), back(dk), back(dv), None, None, None
