@@ -99,11 +99,26 @@ def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
 
 
 def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
-                   engine: Optional[str] = None, dropout_mask=None, delta=None, lse2=None):
-    """-> fp32 (dq, dk, dv) contributions of this block (see ref_attention.attn_block_bwd_ref)."""
+                   engine: Optional[str] = None, dropout_mask=None, delta=None, lse2=None, into=None):
+    """-> (dq, dk, dv) contributions of this block (see ref_attention.attn_block_bwd_ref).
+
+    ``into = (dq, dk, dv, acc_dq, acc_dkv)``: fp32 buffers to write (``acc_*`` False) or accumulate into
+    (``acc_*`` True); the native kernels do the ``+=`` in their epilogue, so a ring step costs no
+    extra pass over the gradients."""
     eng = pick_engine(q, engine)
     if eng == "native" and p.dropout_p == 0.0 and native.has_bwd():
+        if into is not None:
+            dq, dk, dv, acc_dq, acc_dkv = into
+            return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta, lse2=lse2, dq=dq, dk=dk,
+                                   dv=dv, acc_dq=acc_dq, acc_dkv=acc_dkv)
         return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta, lse2=lse2)
+    if into is not None:
+        dq, dk, dv, acc_dq, acc_dkv = into
+        gq, gk, gv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, eng, dropout_mask, delta, lse2)
+        dq.add_(gq) if acc_dq else dq.copy_(gq)
+        dk.add_(gk) if acc_dkv else dk.copy_(gk)
+        dv.add_(gv) if acc_dkv else dv.copy_(gv)
+        return dq, dk, dv
     return ref_attention.attn_block_bwd_ref(
         dout, q, k, v, out, lse, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device),
         p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p,

@@ -209,7 +209,8 @@ def attn_delta(out, dout, lse=None):
 
 
 def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=None, lse2=None,
-             dq=None, dk=None, dv=None, accumulate: bool = False, out_dtype=None, sm_limit: int = 0):
+             dq=None, dk=None, dv=None, accumulate: bool = False, out_dtype=None, sm_limit: int = 0,
+             acc_dq: Optional[bool] = None, acc_dkv: Optional[bool] = None):
     """Backward of one block: two tcgen05 passes (dQ, then dK/dV).  ``lse`` is the FINAL LSE of the
     query rows (may cover more keys than this block: ring steps).  Returns (dq, dk, dv) in
     ``out_dtype`` (default: input dtype; fp32 when ``accumulate``)."""
@@ -217,10 +218,12 @@ def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=N
     q, k, v, dout = _tma_ready(q), _tma_ready(k), _tma_ready(v), _tma_ready(dout)
     if delta is None or lse2 is None:
         delta, lse2 = attn_delta(out, dout, lse)
+    acc_dq = accumulate if acc_dq is None else acc_dq
+    acc_dkv = accumulate if acc_dkv is None else acc_dkv
     if out_dtype is None:
-        out_dtype = torch.float32 if accumulate else q.dtype
+        out_dtype = torch.float32 if (acc_dq or acc_dkv) else q.dtype
     if dq is None:
-        assert not accumulate
+        assert not (acc_dq or acc_dkv)
         dq = torch.empty(q.shape, dtype=out_dtype, device=q.device)
         dk = torch.empty(k.shape, dtype=out_dtype, device=q.device)
         dv = torch.empty(v.shape, dtype=out_dtype, device=q.device)
@@ -233,12 +236,12 @@ def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=N
     for qchunk, kchunk in _chunk_by_group(qrows, krows):
         xq = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in sorted(qchunk, key=lambda r: -r[2])]
         yk = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in kchunk]
-        C.fmha_bwd_pass(False, q, dout, k, v, xq, yk, qs, ks, lse2, delta, dq, None, accumulate,
+        C.fmha_bwd_pass(False, q, dout, k, v, xq, yk, qs, ks, lse2, delta, dq, None, acc_dq,
                         float(p.softmax_scale), wl, wr, float(p.softcap), alibi, int(sm_limit))
         xk = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in kchunk]
         yq = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in qchunk]
         # rows are keys, columns are queries: bounds on (qpos - kpos) are the mirrored window
-        C.fmha_bwd_pass(True, k, v, q, dout, xk, yq, ks, qs, lse2, delta, dk, dv, accumulate,
+        C.fmha_bwd_pass(True, k, v, q, dout, xk, yq, ks, qs, lse2, delta, dk, dv, acc_dkv,
                         float(p.softmax_scale), wr, wl, float(p.softcap), alibi, int(sm_limit))
     return dq, dk, dv
 

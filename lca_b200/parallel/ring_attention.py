@@ -112,7 +112,9 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
     kv_comm, dkv_comm = RingComm(group), RingComm(group)
     k, v = k.contiguous(), v.contiguous()
-    dq = None
+    f32 = dict(dtype=torch.float32, device=q.device)
+    dq = torch.empty(q.shape, **f32)
+    dq_live = False
     dk_acc = dv_acc = next_dk = next_dv = next_k = next_v = None
     for step in range(R):
         if step + 1 != R:
@@ -120,27 +122,27 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
             kv_comm.commit()
         src = (r - step) % R
         k_pos = kpos_of(src)
-        bdk = bdv = None
+        if step > 0:
+            dkv_comm.wait()                       # partial dK/dV of the block we now hold (from the previous rank)
+            dk_acc, dv_acc = next_dk, next_dv
         if block_is_visible(q_pos, k_pos, p):
             dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
-            bdq, bdk, bdv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta, lse2)
-            dq = bdq.to(torch.float32) if dq is None else dq.add_(bdq)
-            bdk, bdv = bdk.to(torch.float32), bdv.to(torch.float32)
-        if step == 0:
-            dk_acc = bdk if bdk is not None else torch.zeros(k.shape, dtype=torch.float32, device=k.device)
-            dv_acc = bdv if bdv is not None else torch.zeros(v.shape, dtype=torch.float32, device=v.device)
-        else:
-            dkv_comm.wait()
-            dk_acc = next_dk if bdk is None else next_dk.add_(bdk)
-            dv_acc = next_dv if bdv is None else next_dv.add_(bdv)
+            if step == 0:
+                dk_acc, dv_acc = torch.empty(k.shape, **f32), torch.empty(v.shape, **f32)
+            # the kernels write / accumulate straight into the fp32 buffers (no extra passes)
+            attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta, lse2,
+                           into=(dq, dk_acc, dv_acc, dq_live, step > 0))
+            dq_live = True
+        elif step == 0:
+            dk_acc, dv_acc = torch.zeros(k.shape, **f32), torch.zeros(v.shape, **f32)
         if step + 1 != R:
             kv_comm.wait()
             k, v = next_k, next_v
         next_dk, next_dv = dkv_comm.send_recv(dk_acc), dkv_comm.send_recv(dv_acc)
         dkv_comm.commit()
     dkv_comm.wait()
-    if dq is None:
-        dq = torch.zeros(q.shape, dtype=torch.float32, device=q.device)
+    if not dq_live:
+        dq.zero_()
     return dq.to(q.dtype), next_dk.to(k.dtype), next_dv.to(v.dtype)
 
 
