@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("LCA_BENCH_MODE", "fwd"), choices=["fwd", "fwdbwd"])
+    ap.add_argument("--mode", default=os.environ.get("LCA_BENCH_MODE", "fwdbwd"), choices=["fwd", "fwdbwd"])
     ap.add_argument("--seq", type=int, default=256 * 1024, help="GLOBAL sequence length")
     ap.add_argument("--heads", type=int, default=8)
     ap.add_argument("--kv-heads", type=int, default=0)
