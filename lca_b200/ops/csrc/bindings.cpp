@@ -185,10 +185,63 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                               at::cuda::getCurrentCUDAStream()));
 }
 
+// mesh = {P, U, R, u, r, rows, n_comm};  qlike/kvlike: user shards to push with their destination byte offsets.
+static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std::vector<at::Tensor>& qlike,
+                      const std::vector<int64_t>& q_offs, const std::vector<at::Tensor>& kvlike,
+                      const std::vector<int64_t>& kv_offs, const c10::optional<at::Tensor>& stat, int64_t stat_off,
+                      int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
+                      const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch, int64_t o_target, int64_t H,
+                      int64_t Hkv) {
+  TORCH_CHECK(mesh.size() == 7, "mesh arity");
+  const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
+  TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
+              static_cast<int>(peer_sigs.size()) == P, "peer tables");
+  c.n_comm = static_cast<int>(mesh[6]);
+  TORCH_CHECK(c.n_comm >= 1 && c.n_comm <= 64, "n_comm");
+  c.P = P; c.U = U; c.R = R;
+  c.u = static_cast<int>(mesh[3]); c.r = static_cast<int>(mesh[4]);
+  c.rows = static_cast<int>(mesh[5]);
+  TORCH_CHECK(qlike.size() <= 2 && kvlike.size() <= 2 && qlike.size() == q_offs.size() && kvlike.size() == kv_offs.size() &&
+              !kvlike.empty(), "push tensor lists");
+  const at::Tensor& k0 = kvlike[0];
+  c.B = static_cast<int>(k0.size(0));
+  c.H = static_cast<int>(H); c.Hkv = static_cast<int>(Hkv); c.D = static_cast<int>(k0.size(3));
+  TORCH_CHECK(c.H % U == 0, "query heads must be divisible by the Ulysses degree");
+  TORCH_CHECK(c.Hkv % U == 0 || U % c.Hkv == 0, "kv heads must divide or be divisible by the Ulysses degree");
+  c.Hl = c.H / U;
+  c.Hkvl = c.Hkv >= U ? c.Hkv / U : 1;
+  auto fill = [&](PushTensor& pt, const at::Tensor& t, int64_t off, int64_t heads) {
+    TORCH_CHECK(t.is_cuda() && t.dim() == 4 && t.size(1) == c.rows && t.size(2) == heads && t.size(3) == c.D &&
+                t.size(0) == c.B, "push shard shape");
+    TORCH_CHECK(t.stride(3) == 1 && t.stride(2) == t.size(3), "push shards need dense (head, dim) axes");
+    TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0 && t.stride(1) % 8 == 0 && t.stride(0) % 8 == 0,
+                "push shards must be 16-byte aligned");
+    pt.src = t.data_ptr(); pt.sb = t.stride(0); pt.ss = t.stride(1); pt.off = off;
+  };
+  c.n_q = static_cast<int>(qlike.size());
+  c.n_kv = static_cast<int>(kvlike.size());
+  for (int i = 0; i < c.n_q; ++i) fill(c.qt[i], qlike[i], q_offs[i], c.H);
+  for (int i = 0; i < c.n_kv; ++i) fill(c.kvt[i], kvlike[i], kv_offs[i], c.Hkv);
+  if (stat.has_value() && stat->defined()) {
+    TORCH_CHECK(stat->scalar_type() == at::kFloat && stat->is_contiguous() && stat->dim() == 3 && stat->size(0) == c.B &&
+                stat->size(1) == c.H && stat->size(2) == c.rows && c.rows % 4 == 0, "stat must be contiguous (B,H,rows) fp32");
+    c.stat = stat->data_ptr<float>();
+    c.stat_off = stat_off;
+  }
+  for (int i = 0; i < P; ++i) {
+    c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
+    c.peer_sig[i] = reinterpret_cast<unsigned int*>(peer_sigs[i]);
+  }
+  c.my_sig = reinterpret_cast<unsigned int*>(my_sig);
+  c.stage_q_rows = stage_q_rows; c.stage_kv_rows = stage_kv_rows;
+  c.epoch = static_cast<unsigned int>(epoch);
+  c.o_target = static_cast<unsigned int>(o_target);
+}
+
 // Fused USP forward: the same kernel with `n_comm` communication CTAs that push this rank's q/k/v shards
 // (`uq`, `uk`, `uv`: user tensors (B, S/P, H|Hkv, D)) into the peers' staging buffers while the compute CTAs
 // consume `q`, `k`, `v` (= views of MY staging buffers, or the user q when U == 1) segment by segment.
-// mesh = {P, U, R, u, r, rows, push_q, n_comm};  offs = {off_q, off_k, off_v, stage_q_rows, stage_kv_rows}
+// mesh = {P, U, R, u, r, rows, n_comm};  offs = {off_q, off_k, off_v, stage_q_rows, stage_kv_rows}
 void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& uq, const at::Tensor& uk,
              const at::Tensor& uv, const std::vector<std::vector<int64_t>>& qsegs,
              const std::vector<std::vector<int64_t>>& ksegs, int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out,
@@ -197,58 +250,29 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
              const std::vector<int64_t>& peer_slabs, const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch,
              int64_t o_target) {
   c10::cuda::CUDAGuard guard(q.device());
-  TORCH_CHECK(mesh.size() == 8 && offs.size() == 5, "mesh/offs arity");
-  const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
-  TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
-              static_cast<int>(peer_sigs.size()) == P, "peer tables");
-  const int n_comm = static_cast<int>(mesh[7]);
-  TORCH_CHECK(n_comm >= 1 && n_comm <= 64, "n_comm");
+  TORCH_CHECK(offs.size() == 5, "offs arity");
   FwdParams p;
+  const int64_t n_comm = mesh.at(6);
   fill_fwd_params(p, q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap,
                   alibi, my_sig, epoch * n_comm);
-  CommParams& c = p.comm;
-  c.n_comm = n_comm;
-  c.P = P; c.U = U; c.R = R;
-  c.u = static_cast<int>(mesh[3]); c.r = static_cast<int>(mesh[4]);
-  c.rows = static_cast<int>(mesh[5]);
-  c.push_q = static_cast<int>(mesh[6]);
-  c.B = static_cast<int>(uq.size(0)); c.H = static_cast<int>(uq.size(2)); c.Hkv = static_cast<int>(uk.size(2));
-  c.D = static_cast<int>(uq.size(3));
-  TORCH_CHECK(uq.size(1) == c.rows && uk.size(1) == c.rows && uv.size(1) == c.rows, "local shard rows");
-  TORCH_CHECK(c.H % U == 0, "query heads must be divisible by the Ulysses degree");
-  TORCH_CHECK(c.Hkv % U == 0 || U % c.Hkv == 0, "kv heads must divide or be divisible by the Ulysses degree");
-  c.Hl = c.H / U;
-  c.Hkvl = c.Hkv >= U ? c.Hkv / U : 1;
-  for (const at::Tensor* t : {&uq, &uk, &uv}) {
-    TORCH_CHECK(t->is_cuda() && t->stride(3) == 1 && t->stride(2) == t->size(3), "q/k/v shards need dense (head, dim) axes");
-    TORCH_CHECK(reinterpret_cast<uintptr_t>(t->data_ptr()) % 16 == 0 && t->stride(1) % 8 == 0 && t->stride(0) % 8 == 0,
-                "q/k/v shards must be 16-byte aligned");
-  }
-  c.q = uq.data_ptr(); c.k = uk.data_ptr(); c.v = uv.data_ptr();
-  c.q_sb = uq.stride(0); c.q_ss = uq.stride(1);
-  c.k_sb = uk.stride(0); c.k_ss = uk.stride(1);
-  c.v_sb = uv.stride(0); c.v_ss = uv.stride(1);
-  for (int i = 0; i < P; ++i) {
-    c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
-    c.peer_sig[i] = reinterpret_cast<unsigned int*>(peer_sigs[i]);
-  }
-  c.my_sig = reinterpret_cast<unsigned int*>(my_sig);
-  c.off_q = offs[0]; c.off_k = offs[1]; c.off_v = offs[2];
-  c.stage_q_rows = offs[3]; c.stage_kv_rows = offs[4];
-  c.epoch = static_cast<unsigned int>(epoch);
-  c.o_target = static_cast<unsigned int>(o_target);
+  std::vector<at::Tensor> ql, kvl = {uk, uv};
+  std::vector<int64_t> qo, kvo = {offs[1], offs[2]};
+  if (mesh.at(1) > 1) { ql.push_back(uq); qo.push_back(offs[0]); }
+  fill_comm(p.comm, mesh, ql, qo, kvl, kvo, c10::nullopt, 0, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
+            o_target, uq.size(2), uk.size(2));
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }
 
 // ------------------------------------------------------------------------------------ fmha bwd
 // One pass of the backward (see fmha_bwd_sm100.cu).  x0/x1 stationary, y0/y1 streamed.
-// xsegs[i] = {row0, nrows, pos0, group, o_row0};  ysegs[i] = {row0, nrows, pos0, flag, group}
-void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
-                   const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
-                   int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
-                   at::Tensor& out0, const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl,
-                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit) {
+// xsegs[i] = {row0, nrows, pos0, group, o_row0 [, flag, o_base0, o_base1, o_sig]};  ysegs[i] = {row0, nrows, pos0, flag, group}
+static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
+                   const at::Tensor& y1, const std::vector<std::vector<int64_t>>& xsegs,
+                   const std::vector<std::vector<int64_t>>& ysegs, int64_t x_pos_stride, int64_t y_pos_stride,
+                   const at::Tensor& lse2, const at::Tensor& delta, at::Tensor& out0, const c10::optional<at::Tensor>& out1,
+                   int64_t out_mode, double scale, int64_t wl, int64_t wr, double softcap,
+                   const c10::optional<at::Tensor>& alibi) {
   TORCH_CHECK(x0.is_cuda() && (x0.scalar_type() == at::kBFloat16 || x0.scalar_type() == at::kHalf), "x0 must be CUDA bf16/fp16");
   for (const at::Tensor* t : {&x1, &y0, &y1}) TORCH_CHECK(t->scalar_type() == x0.scalar_type() && t->is_cuda(), "dtype mismatch");
   const int64_t B = x0.size(0), Hx = x0.size(2), Hy = y0.size(2), D = x0.size(3);
@@ -260,8 +284,6 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
   TORCH_CHECK(lse2.scalar_type() == at::kFloat && delta.scalar_type() == at::kFloat && lse2.dim() == 3 &&
               lse2.sizes() == delta.sizes() && lse2.stride(2) == 1 && delta.strides() == lse2.strides(), "lse2/delta");
   TORCH_CHECK(lse2.size(0) == B && lse2.size(1) == Hq, "lse2 shape");
-  c10::cuda::CUDAGuard guard(x0.device());
-  BwdParams p;
   std::memset(&p, 0, sizeof(p));
   make_tmap(&p.tm_x0, x0, "x0", 128);
   make_tmap(&p.tm_x1, x1, "x1", 128);
@@ -272,10 +294,18 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
   int64_t tiles = 0;
   for (int i = 0; i < p.n_xseg; ++i) {
     const auto& s = xsegs[i];
-    TORCH_CHECK(s.size() == 5 && s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= x0.size(1), "bad xseg");
-    TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out0.size(1), "xseg output rows out of range");
-    p.xseg[i] = {static_cast<int>(s[0]), static_cast<int>(s[1]), static_cast<int>(s[2]), static_cast<int>(s[3]),
-                 static_cast<int>(s[4]), 0};
+    TORCH_CHECK((s.size() == 5 || s.size() == 9) && s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= x0.size(1), "bad xseg");
+    const bool ext = s.size() == 9;
+    if (!ext || s[6] == 0) TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out0.size(1), "xseg output rows out of range");
+    p.xseg[i].row0 = static_cast<int>(s[0]);
+    p.xseg[i].nrows = static_cast<int>(s[1]);
+    p.xseg[i].pos0 = static_cast<int>(s[2]);
+    p.xseg[i].group = static_cast<int>(s[3]);
+    p.xseg[i].o_row0 = static_cast<int>(s[4]);
+    p.xseg[i].flag = ext ? static_cast<int>(s[5]) : -1;
+    p.xseg[i].o_base0 = ext ? reinterpret_cast<void*>(s[6]) : nullptr;
+    p.xseg[i].o_base1 = ext ? reinterpret_cast<void*>(s[7]) : nullptr;
+    p.xseg[i].o_sig = ext ? reinterpret_cast<uint32_t*>(s[8]) : nullptr;
     tiles += (s[1] + 127) / 128;
   }
   for (int i = 0; i < p.n_yseg; ++i) {
@@ -308,10 +338,10 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
   p.delta = delta.data_ptr<float>();
   p.stat_sb = lse2.stride(0);
   p.stat_sh = lse2.stride(1);
-  TORCH_CHECK(out0.dim() == 4 && out0.size(0) == B && out0.size(2) == Hx && out0.size(3) == D && out0.stride(3) == 1, "out0 shape");
+  TORCH_CHECK(out0.dim() == 4 && out0.size(0) == B && out0.size(3) == D && out0.stride(3) == 1, "out0 shape");
   const bool f32 = out0.scalar_type() == at::kFloat;
   TORCH_CHECK(f32 || out0.scalar_type() == x0.scalar_type(), "out dtype");
-  TORCH_CHECK(!accumulate || f32, "accumulate needs fp32 outputs");
+  TORCH_CHECK(out_mode == 0 ? !f32 : f32, "out_mode 1/2/3 need fp32 outputs, mode 0 a 16-bit output");
   p.out0 = out0.data_ptr();
   p.o_sb = out0.stride(0);
   p.o_ss = out0.stride(1);
@@ -323,11 +353,59 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
     p.out1 = out1->data_ptr();
     TORCH_CHECK(reinterpret_cast<uintptr_t>(p.out1) % 16 == 0, "out1 alignment");
   }
-  p.out_mode = f32 ? (accumulate ? 2 : 1) : 0;
+  p.out_mode = static_cast<int>(out_mode);
+}
+
+void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
+                   const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+                   int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
+                   at::Tensor& out0, const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl,
+                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit) {
+  c10::cuda::CUDAGuard guard(x0.device());
+  BwdParams p;
+  const bool f32 = out0.scalar_type() == at::kFloat;
+  TORCH_CHECK(!accumulate || f32, "accumulate needs fp32 outputs");
+  TORCH_CHECK(out0.size(2) == x0.size(2), "out heads");
+  fill_bwd_params(p, is_dkv, x0, x1, y0, y1, xsegs, ysegs, x_pos_stride, y_pos_stride, lse2, delta, out0, out1,
+                  f32 ? (accumulate ? 2 : 1) : 0, scale, wl, wr, softcap, alibi);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
-  LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(D), x0.scalar_type() == at::kBFloat16, is_dkv, sms,
+  LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, sms,
                               at::cuda::getCurrentCUDAStream()));
+}
+
+// Fused USP backward pass.  dQ pass (is_dkv = false) carries the push CTAs (q, dO | k, v | delta) and scatters dQ tiles
+// to the token owners; the dK/dV pass reduces its partial tiles into the owners' fp32 accumulators with red.add over
+// NVLink (out_mode 3).  `out0`/`out1` give the destination layout (strides, dtype); per-segment bases live in xsegs.
+// comm_lists = {} for a pass without push CTAs.
+void usp_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
+                  const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+                  int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
+                  at::Tensor& out0, const c10::optional<at::Tensor>& out1, int64_t out_mode, int64_t o_head_off, double scale,
+                  int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t flags_ptr,
+                  int64_t flag_epoch, const std::vector<int64_t>& mesh, const std::vector<at::Tensor>& qlike,
+                  const std::vector<int64_t>& q_offs, const std::vector<at::Tensor>& kvlike,
+                  const std::vector<int64_t>& kv_offs, const c10::optional<at::Tensor>& stat, int64_t stat_off,
+                  int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
+                  const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch, int64_t o_target, int64_t H,
+                  int64_t Hkv) {
+  c10::cuda::CUDAGuard guard(x0.device());
+  BwdParams p;
+  fill_bwd_params(p, is_dkv, x0, x1, y0, y1, xsegs, ysegs, x_pos_stride, y_pos_stride, lse2, delta, out0, out1, out_mode,
+                  scale, wl, wr, softcap, alibi);
+  p.o_head_off = static_cast<int>(o_head_off);
+  p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
+  p.flag_epoch = static_cast<uint32_t>(flag_epoch);
+  if (!mesh.empty())
+    fill_comm(p.comm, mesh, qlike, q_offs, kvlike, kv_offs, stat, stat_off, stage_q_rows, stage_kv_rows, peer_slabs,
+              peer_sigs, my_sig, epoch, o_target, H, Hkv);
+  LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, num_sms(),
+                              at::cuda::getCurrentCUDAStream()));
+}
+
+void symm_wait(int64_t sig_ptr, int64_t target) {
+  LCA_CUDA_OK(launch_wait_counter(reinterpret_cast<const uint32_t*>(sig_ptr), static_cast<uint32_t>(target),
+                                  at::cuda::getCurrentCUDAStream()));
 }
 
 // ------------------------------------------------------------------------------------ utilities
@@ -434,6 +512,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lca_b200 sm_100a kernels";
   m.def("fmha_fwd", &lca::fmha_fwd, "tcgen05 flash-attention forward (segments + global positions)");
   m.def("usp_fwd", &lca::usp_fwd, "fused USP forward: NVLink push CTAs + tcgen05 attention CTAs in one kernel");
+  m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
+  m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
   m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");
   m.def("finalize_out", &lca::finalize_out, "fp32 accumulator -> 16-bit output");

@@ -25,6 +25,7 @@
 
 #include "fmha_params.h"
 #include "sm100_ptx.cuh"
+#include "usp_comm.cuh"
 
 namespace lca {
 using namespace ptx;
@@ -80,9 +81,10 @@ __device__ __forceinline__ bool decode_work(const BwdParams& p, int w, Work& wk)
   return false;
 }
 
-__device__ __forceinline__ int sched_work(int round) {
-  const int G = gridDim.x;
-  const int c = (round & 1) ? (G - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
+__device__ __forceinline__ int sched_work(int round, int n_comm) {
+  const int G = static_cast<int>(gridDim.x) - n_comm;
+  const int me = static_cast<int>(blockIdx.x) - n_comm;
+  const int c = (round & 1) ? (G - 1 - me) : me;
   return round * G + c;
 }
 
@@ -146,6 +148,16 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
       w.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * mul, __uint_as_float(o[g * 8 + 7]) * mul);
       dst[g] = w;
     }
+  } else if (mode == 3) {
+    // cross-rank reduction: fp32 vector reductions straight into the owner's accumulator (NVLink)
+    float* dst = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + col0 * 4);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4),
+                   "f"(__uint_as_float(o[g * 4 + 0]) * mul), "f"(__uint_as_float(o[g * 4 + 1]) * mul),
+                   "f"(__uint_as_float(o[g * 4 + 2]) * mul), "f"(__uint_as_float(o[g * 4 + 3]) * mul)
+                   : "memory");
+    }
   } else {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(base) + col0 * 4);
 #pragma unroll
@@ -166,6 +178,10 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 template <int kD, bool kBf16, bool kIsDKV>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
+  if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
+    comm_cta(p.comm);
+    return;
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
@@ -221,8 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       uint32_t xc = 0, yc = 0;
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round), wk)) break;
+        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
         if (lane == 0) {
+          wait_arrival(p.flags, p.flag_epoch, p.xseg[wk.xseg].flag);
           mbar_wait(x_empty, (xc & 1) ^ 1);
           mbar_arrive_expect_tx(x_full, 2 * C::XTILE_BYTES);
 #pragma unroll
@@ -239,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           const uint32_t st = yc % C::STAGES;
           const uint32_t par = (yc / C::STAGES) & 1;
           if (lane == 0) {
+            wait_arrival(p.flags, p.flag_epoch, it.flag);
             mbar_wait(y_empty + 8 * st, par ^ 1);
             mbar_arrive_expect_tx(y_full + 8 * st, 2 * C::YTILE_BYTES);
 #pragma unroll
@@ -250,6 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             }
           }
           if constexpr (kIsDKV) {
+            __syncwarp();                      // lane 0 has acquired the arrival flag of this tile's rows
             mbar_wait(st_empty + 8 * st, par ^ 1);
             const float* l2 = p.lse2 + wk.b * p.stat_sb + hy * p.stat_sh;
             const float* dl = p.delta + wk.b * p.stat_sb + hy * p.stat_sh;
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         };
         for (int round = 0;; ++round) {
           Work wk;
-          if (!decode_work(p, sched_work(round), wk)) break;
+          if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
           TileIter it;
           it.init(p, wk);
           mbar_wait(x_full, xc & 1);
@@ -371,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
-      if (!decode_work(p, sched_work(round), wk)) break;
+      if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
       const int xpos = wk.pos0 + row * p.x_pos_stride;
       const int xhi = wk.pos0 + (BX - 1) * p.x_pos_stride;
       const bool row_ok = row < wk.nrows;
@@ -495,15 +514,17 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         if constexpr (kIsDKV) {
           ncols = kD; col_begin = 0;
           tacc = tmem + lane_base + (wg == 0 ? C::TMEM_ACC0 : C::TMEM_ACC1);
-          obase = reinterpret_cast<uint8_t*>(wg == 0 ? p.out0 : p.out1);
+          void* ob = wg == 0 ? (xs.o_base0 ? xs.o_base0 : p.out0) : (xs.o_base1 ? xs.o_base1 : p.out1);
+          obase = reinterpret_cast<uint8_t*>(ob);
           mul = wg == 0 ? p.scale : 1.f;
         } else {
           ncols = kD / 2; col_begin = wg * (kD / 2);
           tacc = tmem + lane_base + C::TMEM_ACC0;
-          obase = reinterpret_cast<uint8_t*>(p.out0);
+          obase = reinterpret_cast<uint8_t*>(xs.o_base0 ? xs.o_base0 : p.out0);
           mul = p.scale;
         }
-        uint8_t* orow_ptr = obase + esz * (wk.b * p.o_sb + orow * p.o_ss + static_cast<int64_t>(wk.hx) * p.o_sh);
+        uint8_t* orow_ptr = obase + esz * (wk.b * p.o_sb + orow * p.o_ss + static_cast<int64_t>(wk.hx + p.o_head_off) * p.o_sh);
+        const bool skip_store = (p.out_mode == 3) && (j == 0);      // nothing to reduce: no visible tile
         for (int c = 0; c < ncols; c += 32) {
           uint32_t o[32];
           if (j > 0) {
@@ -513,7 +534,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = 0u;
           }
-          if (row_ok) store_slice<kBf16>(orow_ptr, col_begin + c, o, mul, p.out_mode);
+          if (row_ok && !skip_store) store_slice<kBf16>(orow_ptr, col_begin + c, o, mul, p.out_mode);
+        }
+        if (xs.o_sig != nullptr) {          // publish this warpgroup's part of the tile to the owner rank
+          __threadfence_system();
+          named_bar_sync(1 + wg, 128);
+          if ((warp & 3) == 0 && lane == 0) red_add_release_sys(xs.o_sig, 1u);
         }
       }
       tc_fence_before();

@@ -20,6 +20,7 @@
 
 #include "fmha_params.h"
 #include "sm100_ptx.cuh"
+#include "usp_comm.cuh"
 
 namespace lca {
 using namespace ptx;
@@ -122,12 +123,7 @@ struct TileIter {
 };
 
 __device__ __forceinline__ void wait_flag(const FwdParams& p, int idx) {
-  if (idx < 0) return;
-  const uint32_t* f = p.flags + idx;
-  while (static_cast<int32_t>(ld_acquire_sys(f) - p.flag_epoch) < 0) {
-    __nanosleep(64);
-  }
-  fence_proxy_async();   // order the acquire before the async-proxy (TMA) reads that follow
+  wait_arrival(p.flags, p.flag_epoch, idx);
 }
 
 template <bool kBf16>
@@ -138,100 +134,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   } else {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Communication CTAs of the fused USP kernel.
-// For every destination sp-rank d (self first, then rotated so NVSwitch ports are evenly loaded):
-//   wait until d has entered this call (ready-to-receive flag), copy my K/V head-slice for d -- and my
-//   Q head-slice if d is in my Ulysses group -- into d's staging with 16-byte st.global over NVLink,
-//   then fence.sys + red.release.sys on d's arrival counters.  The compute CTAs of d poll those
-//   counters with ld.acquire.sys right before the TMA loads of the matching segment.
-struct CopyMsg {
-  const unsigned char* src;
-  unsigned char* dst;
-  long long src_sb, src_ss, dst_sb, dst_ss;   // bytes
-  int nrows, row_vecs;                        // rows per batch, 16-byte vectors per row
-};
-
-__device__ __forceinline__ void comm_copy(const CopyMsg& m, int B, int tid, int nthreads) {
-  const long long total = static_cast<long long>(B) * m.nrows * m.row_vecs;
-  constexpr int UNR = 4;
-  for (long long base = static_cast<long long>(tid) * UNR; base < total; base += static_cast<long long>(nthreads) * UNR) {
-    uint4 val[UNR];
-    long long doff[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; ++j) {
-      const long long i = base + j;
-      doff[j] = -1;
-      if (i < total) {
-        const int c = static_cast<int>(i % m.row_vecs);
-        const long long br = i / m.row_vecs;
-        const int row = static_cast<int>(br % m.nrows);
-        const int b = static_cast<int>(br / m.nrows);
-        val[j] = *reinterpret_cast<const uint4*>(m.src + b * m.src_sb + row * m.src_ss + c * 16);
-        doff[j] = b * m.dst_sb + row * m.dst_ss + c * 16;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; ++j)
-      if (doff[j] >= 0) *reinterpret_cast<uint4*>(m.dst + doff[j]) = val[j];
-  }
-}
-
-__device__ void comm_cta(const FwdParams& p) {
-  const CommParams& c = p.comm;
-  const int tid = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int nthreads = c.n_comm * blockDim.x;
-  const int me = c.r * c.U + c.u;
-  const int esz = 2;
-  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < c.P)      // tell every peer my staging is free for this call
-    st_release_sys(c.peer_sig[threadIdx.x] + kSigRTR + me, c.epoch);
-  const long long row_off_kv = static_cast<long long>(c.r) * c.U * c.rows + static_cast<long long>(c.u) * c.rows;
-  const long long row_off_q = static_cast<long long>(c.u) * c.rows;
-  for (int i = 0; i < c.P; ++i) {
-    const int d = (me + i) % c.P;
-    const int du = d % c.U, dr = d / c.U;
-    if (threadIdx.x == 0) {
-      while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigRTR + d) - c.epoch) < 0) __nanosleep(32);
-    }
-    __syncthreads();
-    // K and V head-slice of destination du: kv head(s) [h0, h0 + Hkvl)
-    const int h0 = (c.Hkv >= c.U) ? du * c.Hkvl : (du * c.Hkv) / c.U;
-    CopyMsg m;
-    m.nrows = c.rows;
-    m.row_vecs = c.Hkvl * c.D * esz / 16;
-    m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
-    m.dst_sb = c.stage_kv_rows * m.dst_ss;
-    m.src = static_cast<const unsigned char*>(c.k) + static_cast<long long>(h0) * c.D * esz;
-    m.src_sb = c.k_sb * esz; m.src_ss = c.k_ss * esz;
-    m.dst = c.peer_slab[d] + c.off_k + row_off_kv * m.dst_ss;
-    comm_copy(m, c.B, tid, nthreads);
-    m.src = static_cast<const unsigned char*>(c.v) + static_cast<long long>(h0) * c.D * esz;
-    m.src_sb = c.v_sb * esz; m.src_ss = c.v_ss * esz;
-    m.dst = c.peer_slab[d] + c.off_v + row_off_kv * m.dst_ss;
-    comm_copy(m, c.B, tid, nthreads);
-    const bool send_q = c.push_q && dr == c.r;
-    if (send_q) {
-      m.row_vecs = c.Hl * c.D * esz / 16;
-      m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
-      m.dst_sb = c.stage_q_rows * m.dst_ss;
-      m.src = static_cast<const unsigned char*>(c.q) + static_cast<long long>(du) * c.Hl * c.D * esz;
-      m.src_sb = c.q_sb * esz; m.src_ss = c.q_ss * esz;
-      m.dst = c.peer_slab[d] + c.off_q + row_off_q * m.dst_ss;
-      comm_copy(m, c.B, tid, nthreads);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
-      if (send_q) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
-    }
-  }
-  // my output buffer is complete once every compute rank has scattered its O tiles into it
-  if (blockIdx.x == 0 && threadIdx.x == 0 && c.o_target != 0) {
-    while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigODone) - c.o_target) < 0) __nanosleep(64);
   }
 }
 
@@ -246,7 +148,7 @@ template <int kD, bool kBf16>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
-    comm_cta(p);
+    comm_cta(p.comm);
     return;
   }
   extern __shared__ uint8_t smem_raw[];

@@ -41,21 +41,29 @@ constexpr int kSigRTR = 32;      // [kSigRTR + dst]  : `dst` entered call `epoch
 constexpr int kSigODone = 48;    // output tiles written into my out buffer by all compute ranks (cumulative)
 constexpr int kSigSlots = 64;
 
-// The communication half of the fused USP kernel: CTAs [0, n_comm) push this rank's Q/K/V
-// head-slices into the peers' staging buffers with plain st.global over NVLink.
+// The communication half of the fused USP kernels: CTAs [0, n_comm) push this rank's shards into the
+// peers' staging buffers with plain st.global over NVLink (see usp_comm.cuh).
+//   "Q-like" tensors (q, and dO in the backward) go to the Ulysses peers of my ring index,
+//   "KV-like" tensors (k, v) go to every sp-rank, optionally a per-row fp32 statistic (delta) rides with Q.
+struct PushTensor {
+  const void* src;                   // (B, rows, heads, D) shard, (head, dim) dense
+  long long sb, ss;                  // element strides (batch, row)
+  long long off;                     // byte offset of the destination staging tensor inside a slab
+};
+
 struct CommParams {
   int n_comm;                        // 0: no comm role (plain single-device attention)
   int P, U, R, u, r;                 // mesh: sp size, degrees, my coordinates; sp-rank = r*U + u
   int rows;                          // local tokens S/P
   int B, H, Hkv, D;
   int Hl, Hkvl;                      // heads per destination (Hkvl = max(1, Hkv/U))
-  int push_q;                        // 0 when U == 1 (Q is read in place)
-  const void *q, *k, *v;             // my shards (B, rows, H|Hkv, D), last two dims dense
-  long long q_sb, q_ss, k_sb, k_ss, v_sb, v_ss;   // element strides (batch, row)
+  int n_q, n_kv;                     // number of Q-like (0 when U == 1) and KV-like tensors to push
+  PushTensor qt[2], kvt[2];
+  const float* stat;                 // optional (B, H, rows) fp32 statistic pushed with the Q-like tensors
+  long long stat_off;                // byte offset of the destination (B, Hl, S/R) fp32 tensor
   unsigned char* peer_slab[kMaxPeers];   // mapped base of every sp-rank's slab (index = sp-rank)
   unsigned int* peer_sig[kMaxPeers];     // mapped signal pad of every sp-rank
   unsigned int* my_sig;
-  long long off_q, off_k, off_v;     // byte offsets of the staging tensors inside a slab
   long long stage_q_rows, stage_kv_rows;   // rows of the staging tensors (S/R and S)
   unsigned int epoch;                // 1-based call counter
   unsigned int o_target;             // value kSigODone must reach before this rank's kernel may exit (0: skip)
@@ -91,7 +99,10 @@ struct XSegD {
   int pos0;
   int group;
   int o_row0;    // first destination row in out0/out1
-  int pad;
+  int flag;      // arrival flag of the stationary rows (-1: none)
+  void* o_base0; // per-segment destination (nullptr: BwdParams::out0 / out1); may be peer-mapped
+  void* o_base1;
+  uint32_t* o_sig;   // optional system-scope completion counter (+1 per finished 128-row tile and warpgroup)
 };
 
 // One parameter block serves both passes (see fmha_bwd_sm100.cu):
@@ -118,7 +129,11 @@ struct BwdParams {
   void* out0;                         // dQ (dQ pass) / dK (dKV pass)
   void* out1;                         // dV (dKV pass)
   int64_t o_sb, o_ss, o_sh;           // output strides in elements
-  int out_mode;                       // 0: 16-bit store, 1: fp32 store, 2: fp32 accumulate
+  int out_mode;                       // 0: 16-bit store, 1: fp32 store, 2: fp32 accumulate, 3: fp32 red.add (peer reduction)
+  int o_head_off;                     // destination head index = hx + o_head_off
+  const uint32_t* flags;              // arrival flags (fused path)
+  uint32_t flag_epoch;
+  CommParams comm;
 };
 
 }  // namespace lca

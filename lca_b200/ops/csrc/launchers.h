@@ -30,6 +30,8 @@ cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* de
                          int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t do_sb, int64_t do_ss, int64_t do_sh,
                          cudaStream_t stream);
 
+cudaError_t launch_wait_counter(const uint32_t* sig, uint32_t target, cudaStream_t stream);
+
 // tensor-map helper (tma_host.cpp part of bindings): 4-D (D, H, S, B) 16-bit tensor, box (64,1,128,1), SWIZZLE_128B
 bool encode_tmap_4d(CUtensorMap* out, const void* base, int64_t D, int64_t H, int64_t S, int64_t B, int64_t stride_h,
                     int64_t stride_s, int64_t stride_b, int box_rows, const char** err);

@@ -1,0 +1,121 @@
+// Communication CTAs of the fused USP kernels (shared by forward and backward).
+//
+// For every destination sp-rank d (self first, then rotated so NVSwitch ports are evenly loaded):
+//   wait until d has entered this call (ready-to-receive flag), copy my KV-like head-slices for d -- and my
+//   Q-like head-slices (+ per-row statistic) if d is in my Ulysses group -- into d's staging with 16-byte
+//   st.global over NVLink, then fence.sys + red.release.sys on d's arrival counters.  The compute CTAs of d
+//   poll those counters with ld.acquire.sys right before the TMA loads of the matching segment.
+#pragma once
+#include "fmha_params.h"
+#include "sm100_ptx.cuh"
+
+namespace lca {
+
+struct CopyMsg {
+  const unsigned char* src;
+  unsigned char* dst;
+  long long src_sb, src_ss, dst_sb, dst_ss;   // bytes
+  int nrows, row_vecs;                        // rows per batch, 16-byte vectors per row
+};
+
+__device__ __forceinline__ void comm_copy(const CopyMsg& m, int B, int tid, int nthreads) {
+  const long long total = static_cast<long long>(B) * m.nrows * m.row_vecs;
+  constexpr int UNR = 4;
+  for (long long base = static_cast<long long>(tid) * UNR; base < total; base += static_cast<long long>(nthreads) * UNR) {
+    uint4 val[UNR];
+    long long doff[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const long long i = base + j;
+      doff[j] = -1;
+      if (i < total) {
+        const int c = static_cast<int>(i % m.row_vecs);
+        const long long br = i / m.row_vecs;
+        const int row = static_cast<int>(br % m.nrows);
+        const int b = static_cast<int>(br / m.nrows);
+        val[j] = *reinterpret_cast<const uint4*>(m.src + b * m.src_sb + row * m.src_ss + c * 16);
+        doff[j] = b * m.dst_sb + row * m.dst_ss + c * 16;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j)
+      if (doff[j] >= 0) *reinterpret_cast<uint4*>(m.dst + doff[j]) = val[j];
+  }
+}
+
+static __device__ __noinline__ void comm_cta(const CommParams& c) {
+  using namespace ptx;
+  const int tid = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int nthreads = c.n_comm * blockDim.x;
+  const int me = c.r * c.U + c.u;
+  const int esz = 2;
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < c.P)      // tell every peer my staging is free for this call
+    st_release_sys(c.peer_sig[threadIdx.x] + kSigRTR + me, c.epoch);
+  const long long row_off_kv = (static_cast<long long>(c.r) * c.U + c.u) * c.rows;
+  const long long row_off_q = static_cast<long long>(c.u) * c.rows;
+  for (int i = 0; i < c.P; ++i) {
+    const int d = (me + i) % c.P;
+    const int du = d % c.U, dr = d / c.U;
+    if (threadIdx.x == 0) {
+      while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigRTR + d) - c.epoch) < 0) __nanosleep(32);
+    }
+    __syncthreads();
+    CopyMsg m;
+    // KV-like head-slice of destination du: kv head(s) [h0, h0 + Hkvl)
+    const int h0 = (c.Hkv >= c.U) ? du * c.Hkvl : (du * c.Hkv) / c.U;
+    m.nrows = c.rows;
+    m.row_vecs = c.Hkvl * c.D * esz / 16;
+    m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
+    m.dst_sb = c.stage_kv_rows * m.dst_ss;
+    for (int t = 0; t < c.n_kv; ++t) {
+      m.src = static_cast<const unsigned char*>(c.kvt[t].src) + static_cast<long long>(h0) * c.D * esz;
+      m.src_sb = c.kvt[t].sb * esz; m.src_ss = c.kvt[t].ss * esz;
+      m.dst = c.peer_slab[d] + c.kvt[t].off + row_off_kv * m.dst_ss;
+      comm_copy(m, c.B, tid, nthreads);
+    }
+    const bool send_q = c.n_q > 0 && dr == c.r;
+    if (send_q) {
+      m.row_vecs = c.Hl * c.D * esz / 16;
+      m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
+      m.dst_sb = c.stage_q_rows * m.dst_ss;
+      for (int t = 0; t < c.n_q; ++t) {
+        m.src = static_cast<const unsigned char*>(c.qt[t].src) + static_cast<long long>(du) * c.Hl * c.D * esz;
+        m.src_sb = c.qt[t].sb * esz; m.src_ss = c.qt[t].ss * esz;
+        m.dst = c.peer_slab[d] + c.qt[t].off + row_off_q * m.dst_ss;
+        comm_copy(m, c.B, tid, nthreads);
+      }
+      if (c.stat != nullptr) {     // (B, H, rows) fp32 -> destination (B, Hl, S/R) at column u*rows
+        CopyMsg s;
+        s.nrows = c.Hl;
+        s.row_vecs = c.rows * 4 / 16;
+        s.src = reinterpret_cast<const unsigned char*>(c.stat) + static_cast<long long>(du) * c.Hl * c.rows * 4;
+        s.src_sb = static_cast<long long>(c.H) * c.rows * 4;
+        s.src_ss = static_cast<long long>(c.rows) * 4;
+        s.dst = c.peer_slab[d] + c.stat_off + row_off_q * 4;
+        s.dst_sb = static_cast<long long>(c.Hl) * c.stage_q_rows * 4;
+        s.dst_ss = c.stage_q_rows * 4;
+        comm_copy(s, c.B, tid, nthreads);
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
+      if (send_q) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
+    }
+  }
+  // my output buffer is complete once every compute rank has scattered its tiles into it
+  if (blockIdx.x == 0 && threadIdx.x == 0 && c.o_target != 0) {
+    while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigODone) - c.o_target) < 0) __nanosleep(64);
+  }
+}
+
+__device__ __forceinline__ void wait_arrival(const uint32_t* flags, uint32_t epoch, int idx) {
+  using namespace ptx;
+  if (idx < 0) return;
+  const uint32_t* f = flags + idx;
+  while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0) __nanosleep(64);
+  fence_proxy_async();   // order the acquire before the async-proxy (TMA) reads that follow
+}
+
+}  // namespace lca

@@ -173,6 +173,16 @@ __global__ void delta_kernel(const T* __restrict__ out, const T* __restrict__ do
   }
 }
 
+// spin (device side, stream ordered) until a monotonic system-scope counter reaches `target`
+__global__ void wait_counter_kernel(const uint32_t* sig, uint32_t target) {
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sig) : "memory");
+    if (static_cast<int32_t>(v - target) >= 0) break;
+    __nanosleep(100);
+  } while (true);
+}
+
 inline int grid_for(int64_t work_items, int threads) {
   int64_t g = (work_items + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -231,6 +241,11 @@ cudaError_t launch_permute_heads_in(const void* src, void* dst, int B, int S, in
   const int64_t BS = static_cast<int64_t>(B) * S;
   const int xv = x_bytes / 16;
   permute_kernel<false><<<grid_for(BS * G * xv, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), BS, G, xv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wait_counter(const uint32_t* sig, uint32_t target, cudaStream_t stream) {
+  wait_counter_kernel<<<1, 1, 0, stream>>>(sig, target);
   return cudaGetLastError();
 }
 

@@ -22,8 +22,11 @@ All counters are monotonic "epochs" -- nothing is reset between calls, so there 
 kernel on the hot path; the only cross-rank handshake is a ready-to-receive flag written at the
 top of each call.
 
-Backward currently reuses the collective path (NCCL all-to-all + P2P ring around the tcgen05
-backward kernels); the saved LSE is produced in exactly the layout that path expects.
+Backward (``LCA_B200_FUSED_BWD=1``, default): dQ pass kernel = push CTAs (q, dO, k, v, delta) + tcgen05 dQ
+tiles scattered to the token owners; dK/dV pass kernel reduces its partial tiles into the owners' fp32
+accumulators with ``red.global.add.v4.f32`` over NVLink (replaces the R-hop fp32 dK/dV ring of
+``ring_flash_attn.py:141-145``).  ``LCA_B200_FUSED_BWD=0`` falls back to the collective backward (NCCL
+all-to-all + P2P ring around the same tcgen05 backward kernels).
 """
 from __future__ import annotations
 
@@ -39,7 +42,7 @@ from ..ops.attention import AttnParams
 from .layout import Seg, canonical_variant, ring_positions, slice_pos
 
 SIG_BYTES = 4096
-SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE = 0, 16, 32, 48
+SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE, SIG_DKV = 0, 16, 32, 48, 49
 MAX_PEERS = 16
 _ALIGN = 1024
 
@@ -86,7 +89,9 @@ class FusedUSPEngine:
         self.key = None
         self.epoch = 0
         self.o_total = 0
+        self.dkv_total = 0
         self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "8"))
+        self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
         self.sig = _Slab(SIG_BYTES, sp_group, device)
 
@@ -100,11 +105,17 @@ class FusedUSPEngine:
         sq = B * (U * rows) * Hl * D * esz if U > 1 else 0
         skv = B * (self.P * rows) * Hkvl * D * esz
         so = B * rows * H * D * esz if U > 1 else 0
+        sdelta = B * Hl * (U * rows) * 4 if U > 1 else 0
+        sdkv = B * rows * Hkv * D * 4 if self.with_bwd else 0
         self.off_q = 0
         self.off_k = _align(self.off_q + sq)
         self.off_v = _align(self.off_k + skv)
-        self.off_o = _align(self.off_v + skv)
-        total = _align(self.off_o + so) + _ALIGN
+        self.off_o = _align(self.off_v + skv)                 # out (fwd) / dq (bwd)
+        self.off_do = _align(self.off_o + so)                  # dO stage (bwd)
+        self.off_delta = _align(self.off_do + (sq if self.with_bwd else 0))
+        self.off_dk = _align(self.off_delta + (sdelta if self.with_bwd else 0))
+        self.off_dv = _align(self.off_dk + sdkv)
+        total = _align(self.off_dv + sdkv) + _ALIGN
         if self.slab is None or self.slab.nbytes < total:
             if self.slab is not None:
                 torch.cuda.synchronize(self.device)
@@ -142,37 +153,11 @@ class FusedUSPEngine:
             out_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
         lse = torch.empty((B, Hl, Sr), dtype=torch.float32, device=q.device)
 
-        # ---- segments (positions of the gathered sequence of ring rank r, split by source shard)
-        qsegs = []
-        n_my_tiles = 0
-        my_ring_pos = ring_positions(variant, r, R, Sr)
-        for su in range(U):
-            owner = r * U + su
-            for s, row0 in _slices_with_rows(my_ring_pos, su * rows, (su + 1) * rows):
-                if push_q:
-                    o_base = slab.peer_ptrs[owner] + self.off_o
-                    o_sig = self.sig.peer_ptrs[owner] + 4 * SIG_ODONE
-                    flag = SIG_Q + su
-                else:
-                    o_base, o_sig, flag = 0, 0, -1
-                qsegs.append([row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0])
-                if su == u:
-                    n_my_tiles += (s.count + 127) // 128
-        qsegs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
-        ksegs = []
-        order = [(r - i) % R for i in range(R)]  # own ring block first, then in "ring step" order
-        for sr in order:
-            pos = ring_positions(variant, sr, R, Sr)
-            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
-            for su in us:
-                src = sr * U + su
-                for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
-                    ksegs.append([sr * Sr + row0, s.count, s.start, SIG_KV + src, 0])
+        qsegs, n_my_tiles = self._q_segments(variant, rows, push_q, self.off_o)
+        ksegs = self._k_segments(variant, rows)
         qstride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
-        alibi = p.alibi_slopes
-        if alibi is not None:
-            alibi = alibi.to(device=q.device, dtype=torch.float32)[..., u * Hl:(u + 1) * Hl].contiguous()
+        alibi = self._alibi(p, Hl)
         if push_q:
             self.o_total += U * B * Hl * n_my_tiles
             o_target = self.o_total & 0xFFFFFFFF
@@ -180,11 +165,122 @@ class FusedUSPEngine:
             o_target = 0
         C.usp_fwd(qst, kst, vst, q, k, v, qsegs, ksegs, qstride, qstride, out_local, u * Hl, lse,
                   float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
-                  [P, U, R, u, r, rows, push_q, self.n_comm],
+                  [P, U, R, u, r, rows, self.n_comm],
                   [self.off_q, self.off_k, self.off_v, Sr, P * rows],
                   slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
         out = out_local.clone() if push_q else out_local   # the symmetric out buffer is reused next call
         return out, lse
+
+    # ------------------------------------------------------------------------------ segment builders
+    def _alibi(self, p, Hl):
+        alibi = p.alibi_slopes
+        if alibi is None:
+            return None
+        return alibi.to(device=self.device, dtype=torch.float32)[..., self.u * Hl:(self.u + 1) * Hl].contiguous()
+
+    def _q_segments(self, variant, rows, pushed: bool, off_out: int):
+        """Rows of my gathered Q (ring rank r) split by source shard -> kernel q segments
+        [row0, nrows, pos0, flag, o_row0, o_base, o_sig, group]; also the number of 128-row tiles over MY rows."""
+        U, R, u, r = self.U, self.R, self.u, self.r
+        segs, n_my_tiles = [], 0
+        pos = ring_positions(variant, r, R, U * rows)
+        for su in range(U):
+            owner = r * U + su
+            for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
+                if pushed:
+                    o_base = self.slab.peer_ptrs[owner] + off_out
+                    o_sig = self.sig.peer_ptrs[owner] + 4 * SIG_ODONE
+                    flag = SIG_Q + su
+                else:
+                    o_base, o_sig, flag = 0, 0, -1
+                segs.append([row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0])
+                if su == u:
+                    n_my_tiles += (s.count + 127) // 128
+        segs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
+        return segs, n_my_tiles
+
+    def _k_segments(self, variant, rows):
+        """All K/V rows in my staging (every source shard) -> [row0, nrows, pos0, flag, group], own block first."""
+        U, R, u, r = self.U, self.R, self.u, self.r
+        Sr = U * rows
+        segs = []
+        for sr in [(r - i) % R for i in range(R)]:        # own ring block first, then "ring step" order
+            pos = ring_positions(variant, sr, R, Sr)
+            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
+            for su in us:
+                for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
+                    segs.append([sr * Sr + row0, s.count, s.start, SIG_KV + sr * U + su, 0])
+        return segs
+
+    # ------------------------------------------------------------------------------ backward
+    def backward(self, dout, q, k, v, out, lse, variant: str, p: AttnParams):
+        """Fused backward: dQ pass (with the push CTAs for q, dO, k, v, delta) scatters dQ tiles to the token
+        owners; dK/dV pass reduces its partial tiles into the owners' fp32 accumulators with red.add over NVLink."""
+        C = native.ext()
+        U, R, u, r, P = self.U, self.R, self.u, self.r, self.P
+        B, rows, H, D = q.shape
+        Hkv = k.shape[2]
+        esz = q.element_size()
+        Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
+        q, k, v, dout = (_dense_heads(t) for t in (q, k, v, dout))
+        self._ensure(B, rows, H, Hkv, D, esz)
+        slab = self.slab
+        Sr = U * rows
+        pushed = U > 1
+        delta_local = native.attn_delta(out, dout)                                  # (B, H, rows) fp32
+        lse2 = torch.where(torch.isinf(lse), torch.full_like(lse, float("inf")), lse * 1.4426950408889634)
+        kst = slab.tensor(self.off_k, (B, P * rows, Hkvl, D), q.dtype)
+        vst = slab.tensor(self.off_v, (B, P * rows, Hkvl, D), q.dtype)
+        dk_acc = slab.tensor(self.off_dk, (B, rows, Hkv, D), torch.float32)
+        dv_acc = slab.tensor(self.off_dv, (B, rows, Hkv, D), torch.float32)
+        dk_acc.zero_()
+        dv_acc.zero_()
+        if pushed:
+            qst = slab.tensor(self.off_q, (B, Sr, Hl, D), q.dtype)
+            dost = slab.tensor(self.off_do, (B, Sr, Hl, D), q.dtype)
+            delta_c = slab.tensor(self.off_delta, (B, Hl, Sr), torch.float32)
+            dq_local = slab.tensor(self.off_o, (B, rows, H, D), q.dtype)
+        else:
+            qst, dost, delta_c = q, dout, delta_local
+            dq_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
+        self.epoch += 1
+        fe = self.epoch * self.n_comm
+        qsegs, n_my_tiles = self._q_segments(variant, rows, pushed, self.off_o)
+        ksegs = self._k_segments(variant, rows)
+        stride = R if canonical_variant(variant) == "stripe" else 1
+        wl, wr = native.window_bounds(p)
+        alibi = self._alibi(p, Hl)
+        # ---- pass 1: dQ (+ all pushes)
+        xq = [[s[0], s[1], s[2], s[7], s[4], s[3], s[5], 0, s[6]] for s in qsegs]
+        if pushed:
+            self.o_total += U * B * Hl * n_my_tiles * 2          # two warpgroups publish each tile
+            o_target = self.o_total & 0xFFFFFFFF
+        else:
+            o_target = 0
+        mesh = [P, U, R, u, r, rows, self.n_comm]
+        ql, qo = ([q, dout], [self.off_q, self.off_do]) if pushed else ([], [])
+        C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,
+                       float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe, mesh, ql, qo, [k, v],
+                       [self.off_k, self.off_v], delta_local if pushed else None, self.off_delta, Sr, P * rows,
+                       slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
+        # ---- pass 2: dK/dV for every K/V row I hold, reduced into the owners' accumulators
+        h0 = u * Hkvl if Hkv >= U else (u * Hkv) // U
+        xk, n_my_kv_tiles = [], 0
+        for s in ksegs:
+            src = s[3] - SIG_KV
+            o_row0 = s[0] - src * rows                          # row inside the owner's local shard
+            xk.append([s[0], s[1], s[2], s[4], o_row0, s[3], slab.peer_ptrs[src] + self.off_dk,
+                       slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV])
+            if src == self.me:
+                n_my_kv_tiles += (s[1] + 127) // 128
+        yq = [[s[0], s[1], s[2], s[3], s[7]] for s in qsegs]
+        self.dkv_total += P * B * Hkvl * n_my_kv_tiles * 2
+        C.usp_bwd_pass(True, kst, vst, qst, dost, xk, yq, stride, stride, lse2, delta_c, dk_acc, dv_acc, 3, h0,
+                       float(p.softmax_scale), wr, wl, float(p.softcap), alibi, self.sig.ptr, fe, [], [], [], [], [],
+                       None, 0, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
+        C.symm_wait(self.sig.ptr + 4 * SIG_DKV, self.dkv_total & 0xFFFFFFFF)
+        dq = dq_local.clone() if pushed else dq_local
+        return dq, dk_acc.to(k.dtype), dv_acc.to(v.dtype)
 
     # ------------------------------------------------------------------------------ autograd entry
     def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic):
@@ -232,6 +328,9 @@ class _FusedAttnFunc(torch.autograd.Function):
         from .ring_attention import ring_attn_backward
         q, k, v, out, lse = ctx.saved_tensors
         eng, p = ctx.eng, ctx.p
+        if eng.with_bwd:
+            dq, dk, dv = eng.backward(dout, q, k, v, out, lse, ctx.variant, p)
+            return dq, dk, dv, None, None, None
         ug, rg = eng.ulysses_pg, eng.ring_pg
         if eng.U > 1 and k.shape[2] % eng.U:
             raise NotImplementedError("backward with kv_heads < ulysses degree needs the fused backward (round 2)")
