@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tT0 = tmem + lane_base + C::TMEM_T0 + wg * BY;
     const uint32_t tT1 = tmem + lane_base + C::TMEM_T1 + wg * BY;
-    uint32_t tc = 0, yc = 0, afc = 0;
+    uint32_t tc = 0, yc = 0, afc = 0, xcw = 0;
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -396,6 +396,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       const bool row_ok = row < wk.nrows;
       float lse2_r = INFINITY, delta_r = 0.f;
       if constexpr (!kIsDKV) {
+        // the per-row statistics may have been pushed by a peer together with this Q/dO tile: the producer
+        // acquired the arrival flag before issuing the tile's TMA, so x_full orders our reads after the push
+        mbar_wait(x_full, xcw & 1);
+        ++xcw;
         if (row_ok) {
           lse2_r = p.lse2[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
           delta_r = p.delta[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
@@ -567,8 +571,10 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  int grid = p.total_work < num_sms ? p.total_work : num_sms;
+  const int avail = num_sms - p.comm.n_comm;
+  int grid = p.total_work < avail ? p.total_work : avail;
   if (grid < 1) grid = 1;
+  grid += p.comm.n_comm;       // comm CTAs first; all CTAs are co-resident (1 CTA/SM, grid <= #SMs)
   kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }

@@ -41,16 +41,25 @@ def run_distributed(fn, world, *args, backend="gloo", timeout=300):
     errq = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, backend, fn, args, errq)) for r in range(world)]
+    import time
     for p in procs:
         p.start()
-    for p in procs:
-        p.join(timeout)
+    errs = []
+    t0 = time.time()
+    while any(p.is_alive() for p in procs) and time.time() - t0 < timeout:
+        while not errq.empty():
+            errs.append(errq.get())
+        if errs:                       # fail fast: peers of a dead rank would spin on its flags forever
+            time.sleep(2.0)
+            break
+        time.sleep(0.2)
     hung = [p for p in procs if p.is_alive()]
     for p in hung:
         p.kill()
-    errs = []
     while not errq.empty():
         errs.append(errq.get())
+    if errs:
+        hung = []
     assert not hung, f"{len(hung)} rank(s) hung"
     assert not errs, "\n".join(f"[rank {r}]\n{tb}" for r, tb in errs)
     bad = [p.exitcode for p in procs if p.exitcode != 0]
