@@ -8,8 +8,25 @@
 #pragma once
 #include "fmha_params.h"
 #include "sm100_ptx.cuh"
+#include <cstdio>
 
 namespace lca {
+
+// Spin-wait watchdog: a peer that never arrives (crashed rank, mismatched call sequence) must not hang the
+// GPU forever -- after ~30 s of polling the kernel traps, which surfaces as a CUDA error on the host.
+constexpr unsigned long long kWatchdogPolls = 1ull << 28;
+
+static __device__ __noinline__ void spin_until_ge(const uint32_t* addr, uint32_t target, unsigned ns) {
+  unsigned long long polls = 0;
+  while (static_cast<int32_t>(ptx::ld_acquire_sys(addr) - target) < 0) {
+    __nanosleep(ns);
+    if (++polls > kWatchdogPolls) {
+      printf("[lca_b200] watchdog: flag %p stuck at %u, waiting for %u (block %d)\n", addr, ptx::ld_relaxed_sys(addr),
+             target, static_cast<int>(blockIdx.x));
+      __trap();
+    }
+  }
+}
 
 struct CopyMsg {
   const unsigned char* src;
@@ -57,7 +74,7 @@ static __device__ __noinline__ void comm_cta(const CommParams& c) {
     const int d = (me + i) % c.P;
     const int du = d % c.U, dr = d / c.U;
     if (threadIdx.x == 0) {
-      while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigRTR + d) - c.epoch) < 0) __nanosleep(32);
+      spin_until_ge(c.my_sig + kSigRTR + d, c.epoch, 32);
     }
     __syncthreads();
     CopyMsg m;
@@ -106,15 +123,14 @@ static __device__ __noinline__ void comm_cta(const CommParams& c) {
   }
   // my output buffer is complete once every compute rank has scattered its tiles into it
   if (blockIdx.x == 0 && threadIdx.x == 0 && c.o_target != 0) {
-    while (static_cast<int>(ld_acquire_sys(c.my_sig + kSigODone) - c.o_target) < 0) __nanosleep(64);
+    spin_until_ge(c.my_sig + kSigODone, c.o_target, 64);
   }
 }
 
 __device__ __forceinline__ void wait_arrival(const uint32_t* flags, uint32_t epoch, int idx) {
   using namespace ptx;
   if (idx < 0) return;
-  const uint32_t* f = flags + idx;
-  while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0) __nanosleep(64);
+  spin_until_ge(flags + idx, epoch, 64);
   fence_proxy_async();   // order the acquire before the async-proxy (TMA) reads that follow
 }
 

@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <cstdio>
 #include <type_traits>
 
 #include "launchers.h"
@@ -176,10 +177,15 @@ __global__ void delta_kernel(const T* __restrict__ out, const T* __restrict__ do
 // spin (device side, stream ordered) until a monotonic system-scope counter reaches `target`
 __global__ void wait_counter_kernel(const uint32_t* sig, uint32_t target) {
   uint32_t v;
+  unsigned long long polls = 0;
   do {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sig) : "memory");
     if (static_cast<int32_t>(v - target) >= 0) break;
     __nanosleep(100);
+    if (++polls > (1ull << 28)) {      // ~30 s: a peer never delivered -> fail loudly instead of hanging the GPU
+      printf("[lca_b200] watchdog: counter %p stuck at %u, waiting for %u\n", sig, v, target);
+      __trap();
+    }
   } while (true);
 }
 

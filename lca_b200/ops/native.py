@@ -102,9 +102,17 @@ def why_not(q: torch.Tensor) -> str:
         return "device is not sm_100"
     if q.dtype not in (torch.bfloat16, torch.float16):
         return f"dtype {q.dtype} (need bf16/fp16)"
-    if q.shape[-1] not in SUPPORTED_HEAD_DIMS:
-        return f"head_dim {q.shape[-1]} (supported: {SUPPORTED_HEAD_DIMS})"
+    if q.shape[-1] > max(SUPPORTED_HEAD_DIMS) or q.shape[-1] % 8:
+        return f"head_dim {q.shape[-1]} (native tiles: {SUPPORTED_HEAD_DIMS}; others are zero-padded up to 128)"
     return ""
+
+
+def _padded_dim(D: int) -> int:
+    return next(d for d in SUPPORTED_HEAD_DIMS if d >= D)
+
+
+def _pad_last(t: torch.Tensor, Dp: int) -> torch.Tensor:
+    return t if t.shape[-1] == Dp else torch.nn.functional.pad(t, (0, Dp - t.shape[-1]))
 
 
 def supports(q: torch.Tensor) -> bool:
@@ -153,6 +161,16 @@ def _tma_ready(t: torch.Tensor) -> torch.Tensor:
 def fmha_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p, out=None, lse=None, sm_limit: int = 0):
     """Forward attention of one block with global-position masks.  -> (out, lse)."""
     C = ext()
+    D0 = q.shape[-1]
+    if D0 not in SUPPORTED_HEAD_DIMS:
+        # head dims between the native tile widths run zero-padded (QK^T and PV are unchanged by zero columns;
+        # the softmax scale is explicit in `p`)
+        Dp = _padded_dim(D0)
+        o, l = fmha_fwd(_pad_last(q, Dp), _pad_last(k, Dp), _pad_last(v, Dp), q_pos, k_pos, p, None, lse, sm_limit)
+        if out is not None:
+            out.copy_(o[..., :D0])
+            return out, l
+        return o[..., :D0].contiguous(), l
     q, k, v = _tma_ready(q), _tma_ready(k), _tma_ready(v)
     B, Sq, H, D = q.shape
     if out is None:
@@ -215,6 +233,23 @@ def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=N
     query rows (may cover more keys than this block: ring steps).  Returns (dq, dk, dv) in
     ``out_dtype`` (default: input dtype; fp32 when ``accumulate``)."""
     C = ext()
+    D0 = q.shape[-1]
+    if D0 not in SUPPORTED_HEAD_DIMS:
+        Dp = _padded_dim(D0)
+        if delta is None or lse2 is None:
+            delta, lse2 = attn_delta(out, dout, lse)
+        gq, gk, gv = fmha_bwd(_pad_last(dout, Dp), _pad_last(q, Dp), _pad_last(k, Dp), _pad_last(v, Dp), None, lse,
+                              q_pos, k_pos, p, delta=delta, lse2=lse2, out_dtype=out_dtype or (torch.float32 if (accumulate or acc_dq or acc_dkv) else q.dtype),
+                              sm_limit=sm_limit)
+        gq, gk, gv = gq[..., :D0], gk[..., :D0], gv[..., :D0]
+        if dq is None:
+            return gq.contiguous(), gk.contiguous(), gv.contiguous()
+        a_q = accumulate if acc_dq is None else acc_dq
+        a_kv = accumulate if acc_dkv is None else acc_dkv
+        dq.add_(gq) if a_q else dq.copy_(gq)
+        dk.add_(gk) if a_kv else dk.copy_(gk)
+        dv.add_(gv) if a_kv else dv.copy_(gv)
+        return dq, dk, dv
     q, k, v, dout = _tma_ready(q), _tma_ready(k), _tma_ready(v), _tma_ready(dout)
     if delta is None or lse2 is None:
         delta, lse2 = attn_delta(out, dout, lse)

@@ -364,7 +364,7 @@ def _same_node_p2p(group, device) -> bool:
 
 def _supported_input(q) -> bool:
     return (q.is_cuda and native.available() and q.dtype in (torch.bfloat16, torch.float16)
-            and q.shape[-1] in native.SUPPORTED_HEAD_DIMS)
+            and q.shape[-1] in native.SUPPORTED_HEAD_DIMS)   # padded head dims use the collective path
 
 
 def engine_for_mesh(pgs, q, strict: bool = False):
