@@ -87,7 +87,7 @@ static int num_sms() {
   } while (0)
 
 // ------------------------------------------------------------------------------------ fmha fwd
-// qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr, group}
+// qsegs[i] = {row0, nrows, pos0, flag, o_row0, o_base_ptr (0 -> `out`), o_sig_ptr, group [, lse_owner_ptr]}
 // ksegs[i] = {row0, nrows, pos0, flag, group}
 static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
               const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
@@ -114,7 +114,7 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   int64_t pairs = 0;
   for (int i = 0; i < p.n_qseg; ++i) {
     const auto& s = qsegs[i];
-    TORCH_CHECK(s.size() == 8, "qseg needs 8 fields");
+    TORCH_CHECK(s.size() == 8 || s.size() == 9, "qseg needs 8 or 9 fields");
     TORCH_CHECK(s[0] >= 0 && s[1] > 0 && s[0] + s[1] <= q.size(1), "qseg rows out of range");
     p.qseg[i].row0 = static_cast<int>(s[0]);
     p.qseg[i].nrows = static_cast<int>(s[1]);
@@ -124,6 +124,7 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
     p.qseg[i].o_base = s[5] ? reinterpret_cast<void*>(s[5]) : out.data_ptr();
     p.qseg[i].o_sig = reinterpret_cast<uint32_t*>(s[6]);
     p.qseg[i].group = static_cast<int>(s[7]);
+    p.qseg[i].lse_base = s.size() == 9 ? reinterpret_cast<float*>(s[8]) : nullptr;
     if (!s[5]) TORCH_CHECK(s[4] >= 0 && s[4] + s[1] <= out.size(1), "qseg output rows out of range");
     pairs += (s[1] + 255) / 256;
   }
@@ -168,6 +169,8 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   TORCH_CHECK(lse.size(0) == B && lse.size(1) == H && lse.size(2) >= q.size(1), "lse shape");
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
+  p.lse_own_sb = out.size(2) * out.size(1);      // owners keep (B, H_total, rows) next to their (B, rows, H_total, D) output
+  p.lse_own_sh = out.size(1);
 }
 
 void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
@@ -188,8 +191,8 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
 // mesh = {P, U, R, u, r, rows, n_comm};  qlike/kvlike: user shards to push with their destination byte offsets.
 static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std::vector<at::Tensor>& qlike,
                       const std::vector<int64_t>& q_offs, const std::vector<at::Tensor>& kvlike,
-                      const std::vector<int64_t>& kv_offs, const c10::optional<at::Tensor>& stat, int64_t stat_off,
-                      int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
+                      const std::vector<int64_t>& kv_offs, const std::vector<at::Tensor>& stats,
+                      const std::vector<int64_t>& stat_offs, bool q_to_all, int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
                       const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch, int64_t o_target, int64_t H,
                       int64_t Hkv) {
   TORCH_CHECK(mesh.size() == 7, "mesh arity");
@@ -222,11 +225,15 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
   c.n_kv = static_cast<int>(kvlike.size());
   for (int i = 0; i < c.n_q; ++i) fill(c.qt[i], qlike[i], q_offs[i], c.H);
   for (int i = 0; i < c.n_kv; ++i) fill(c.kvt[i], kvlike[i], kv_offs[i], c.Hkv);
-  if (stat.has_value() && stat->defined()) {
-    TORCH_CHECK(stat->scalar_type() == at::kFloat && stat->is_contiguous() && stat->dim() == 3 && stat->size(0) == c.B &&
-                stat->size(1) == c.H && stat->size(2) == c.rows && c.rows % 4 == 0, "stat must be contiguous (B,H,rows) fp32");
-    c.stat = stat->data_ptr<float>();
-    c.stat_off = stat_off;
+  TORCH_CHECK(stats.size() <= 2 && stats.size() == stat_offs.size(), "stat lists");
+  c.n_stat = static_cast<int>(stats.size());
+  c.q_to_all = q_to_all ? 1 : 0;
+  for (int i = 0; i < c.n_stat; ++i) {
+    const at::Tensor& st = stats[i];
+    TORCH_CHECK(st.scalar_type() == at::kFloat && st.is_contiguous() && st.dim() == 3 && st.size(0) == c.B &&
+                st.size(1) == c.H && st.size(2) == c.rows && c.rows % 4 == 0, "stat must be contiguous (B,H,rows) fp32");
+    c.stat[i] = st.data_ptr<float>();
+    c.stat_off[i] = stat_offs[i];
   }
   for (int i = 0; i < P; ++i) {
     c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
@@ -258,7 +265,7 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
   std::vector<at::Tensor> ql, kvl = {uk, uv};
   std::vector<int64_t> qo, kvo = {offs[1], offs[2]};
   if (mesh.at(1) > 1) { ql.push_back(uq); qo.push_back(offs[0]); }
-  fill_comm(p.comm, mesh, ql, qo, kvl, kvo, c10::nullopt, 0, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
+  fill_comm(p.comm, mesh, ql, qo, kvl, kvo, {}, {}, false, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
             o_target, uq.size(2), uk.size(2));
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
@@ -385,8 +392,9 @@ void usp_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const
                   int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t flags_ptr,
                   int64_t flag_epoch, const std::vector<int64_t>& mesh, const std::vector<at::Tensor>& qlike,
                   const std::vector<int64_t>& q_offs, const std::vector<at::Tensor>& kvlike,
-                  const std::vector<int64_t>& kv_offs, const c10::optional<at::Tensor>& stat, int64_t stat_off,
-                  int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
+                  const std::vector<int64_t>& kv_offs, const std::vector<at::Tensor>& stats,
+                  const std::vector<int64_t>& stat_offs, bool q_to_all, int64_t stage_q_rows, int64_t stage_kv_rows,
+                  const std::vector<int64_t>& peer_slabs,
                   const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch, int64_t o_target, int64_t H,
                   int64_t Hkv) {
   c10::cuda::CUDAGuard guard(x0.device());
@@ -397,8 +405,8 @@ void usp_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
   if (!mesh.empty())
-    fill_comm(p.comm, mesh, qlike, q_offs, kvlike, kv_offs, stat, stat_off, stage_q_rows, stage_kv_rows, peer_slabs,
-              peer_sigs, my_sig, epoch, o_target, H, Hkv);
+    fill_comm(p.comm, mesh, qlike, q_offs, kvlike, kv_offs, stats, stat_offs, q_to_all, stage_q_rows, stage_kv_rows,
+              peer_slabs, peer_sigs, my_sig, epoch, o_target, H, Hkv);
   LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }

@@ -470,6 +470,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       if (row < rows_t) {
         const float lse = (l > 0.f) ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
         p.lse[wk.b * p.lse_sb + wk.h * p.lse_sh + wk.row0 + t * BM + row] = lse;
+        float* lown = p.qseg[wk.qseg].lse_base;     // the token owner keeps the LSE too (used by the fused backward)
+        if (lown != nullptr)
+          lown[wk.b * p.lse_own_sb + static_cast<int64_t>(wk.h + p.o_head_off) * p.lse_own_sh + p.qseg[wk.qseg].o_row0 +
+               wk.seg_row0 + t * BM + row] = lse;
       }
       named_bar_sync(1 + t, 128);
       {

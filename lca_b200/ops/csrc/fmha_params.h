@@ -21,6 +21,7 @@ struct QSegD {
   int group;       // attention group id: a Q segment only visits K segments of the same group (varlen)
   void* o_base;    // output tensor base for this segment (may be a peer-mapped pointer)
   uint32_t* o_sig; // optional: system-scope counter incremented once per finished 128-row tile
+  float* lse_base; // optional: token owner's (B, H_total, rows) fp32 LSE buffer (fused path; may be peer-mapped)
 };
 
 struct KSegD {
@@ -39,7 +40,11 @@ constexpr int kSigKV = 0;        // [kSigKV + src]   : K/V shard of sp-rank `src
 constexpr int kSigQ = 16;        // [kSigQ + src_u]  : Q shard of Ulysses-rank `src_u` landed  (+n_comm per call)
 constexpr int kSigRTR = 32;      // [kSigRTR + dst]  : `dst` entered call `epoch` (its staging may be overwritten)
 constexpr int kSigODone = 48;    // output tiles written into my out buffer by all compute ranks (cumulative)
-constexpr int kSigSlots = 64;
+constexpr int kSigDKV = 49;      // dK/dV tiles (or reductions) delivered into my buffers (cumulative)
+constexpr int kSigQA = 64;       // [kSigQA + src]   : Q-like shard of sp-rank `src` landed in the ALL-ranks staging (+n_comm per call)
+constexpr int kSigSlots = 96;
+// Every call bumps every arrival class (KV, Q, QA) by n_comm, whether or not data of that class was sent, so all
+// classes stay in lock-step with the call epoch and one expected value serves every flag.
 
 // The communication half of the fused USP kernels: CTAs [0, n_comm) push this rank's shards into the
 // peers' staging buffers with plain st.global over NVLink (see usp_comm.cuh).
@@ -58,9 +63,11 @@ struct CommParams {
   int B, H, Hkv, D;
   int Hl, Hkvl;                      // heads per destination (Hkvl = max(1, Hkv/U))
   int n_q, n_kv;                     // number of Q-like (0 when U == 1) and KV-like tensors to push
+  int q_to_all;                      // 1: Q-like tensors (and statistics) go to EVERY sp-rank (backward dK/dV pass)
+  int n_stat;                        // per-row fp32 statistics (B, H, rows) pushed with the Q-like tensors (delta, lse2)
   PushTensor qt[2], kvt[2];
-  const float* stat;                 // optional (B, H, rows) fp32 statistic pushed with the Q-like tensors
-  long long stat_off;                // byte offset of the destination (B, Hl, S/R) fp32 tensor
+  const float* stat[2];
+  long long stat_off[2];             // byte offsets of the destination (B, Hl, stage rows) fp32 tensors
   unsigned char* peer_slab[kMaxPeers];   // mapped base of every sp-rank's slab (index = sp-rank)
   unsigned int* peer_sig[kMaxPeers];     // mapped signal pad of every sp-rank
   unsigned int* my_sig;
@@ -87,6 +94,7 @@ struct FwdParams {
   int o_head_off;                     // destination head index = h + o_head_off
   float* lse;                         // (B, H, lse_rows) fp32, row index = row in the Q tensor
   int64_t lse_sb, lse_sh;
+  int64_t lse_own_sb, lse_own_sh;     // strides of the owners' LSE buffers (QSegD::lse_base), indexed like the output
   const uint32_t* flags;              // arrival flags written by peers (fused paths)
   uint32_t flag_epoch;
   CommParams comm;

@@ -90,27 +90,30 @@ static __device__ __noinline__ void comm_cta(const CommParams& c) {
       m.dst = c.peer_slab[d] + c.kvt[t].off + row_off_kv * m.dst_ss;
       comm_copy(m, c.B, tid, nthreads);
     }
-    const bool send_q = c.n_q > 0 && dr == c.r;
+    const bool have_q = c.n_q > 0 || c.n_stat > 0;
+    const bool send_q = have_q && (c.q_to_all || dr == c.r);
     if (send_q) {
+      const long long q_rows = c.q_to_all ? c.stage_kv_rows : c.stage_q_rows;     // rows of the destination staging
+      const long long q_off = c.q_to_all ? row_off_kv : row_off_q;
       m.row_vecs = c.Hl * c.D * esz / 16;
       m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
-      m.dst_sb = c.stage_q_rows * m.dst_ss;
+      m.dst_sb = q_rows * m.dst_ss;
       for (int t = 0; t < c.n_q; ++t) {
         m.src = static_cast<const unsigned char*>(c.qt[t].src) + static_cast<long long>(du) * c.Hl * c.D * esz;
         m.src_sb = c.qt[t].sb * esz; m.src_ss = c.qt[t].ss * esz;
-        m.dst = c.peer_slab[d] + c.qt[t].off + row_off_q * m.dst_ss;
+        m.dst = c.peer_slab[d] + c.qt[t].off + q_off * m.dst_ss;
         comm_copy(m, c.B, tid, nthreads);
       }
-      if (c.stat != nullptr) {     // (B, H, rows) fp32 -> destination (B, Hl, S/R) at column u*rows
+      for (int t = 0; t < c.n_stat; ++t) {   // (B, H, rows) fp32 -> destination (B, Hl, q_rows) at column q_off
         CopyMsg s;
         s.nrows = c.Hl;
         s.row_vecs = c.rows * 4 / 16;
-        s.src = reinterpret_cast<const unsigned char*>(c.stat) + static_cast<long long>(du) * c.Hl * c.rows * 4;
+        s.src = reinterpret_cast<const unsigned char*>(c.stat[t]) + static_cast<long long>(du) * c.Hl * c.rows * 4;
         s.src_sb = static_cast<long long>(c.H) * c.rows * 4;
         s.src_ss = static_cast<long long>(c.rows) * 4;
-        s.dst = c.peer_slab[d] + c.stat_off + row_off_q * 4;
-        s.dst_sb = static_cast<long long>(c.Hl) * c.stage_q_rows * 4;
-        s.dst_ss = c.stage_q_rows * 4;
+        s.dst = c.peer_slab[d] + c.stat_off[t] + q_off * 4;
+        s.dst_sb = static_cast<long long>(c.Hl) * q_rows * 4;
+        s.dst_ss = q_rows * 4;
         comm_copy(s, c.B, tid, nthreads);
       }
     }
@@ -118,7 +121,8 @@ static __device__ __noinline__ void comm_cta(const CommParams& c) {
     __syncthreads();
     if (threadIdx.x == 0) {
       red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
-      if (send_q) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
+      if (dr == c.r) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
+      red_add_release_sys(c.peer_sig[d] + kSigQA + me, 1u);
     }
   }
   // my output buffer is complete once every compute rank has scattered its tiles into it

@@ -42,7 +42,7 @@ from ..ops.attention import AttnParams
 from .layout import Seg, canonical_variant, ring_positions, slice_pos
 
 SIG_BYTES = 4096
-SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE, SIG_DKV = 0, 16, 32, 48, 49
+SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE, SIG_DKV, SIG_QA = 0, 16, 32, 48, 49, 64
 MAX_PEERS = 16
 _ALIGN = 1024
 
@@ -102,20 +102,23 @@ class FusedUSPEngine:
         key = (B, rows, H, Hkv, D, esz)
         if key == self.key:
             return
-        sq = B * (U * rows) * Hl * D * esz if U > 1 else 0
-        skv = B * (self.P * rows) * Hkvl * D * esz
-        so = B * rows * H * D * esz if U > 1 else 0
-        sdelta = B * Hl * (U * rows) * 4 if U > 1 else 0
-        sdkv = B * rows * Hkv * D * 4 if self.with_bwd else 0
+        S = self.P * rows
+        sq = B * (S if self.with_bwd else U * rows) * Hl * D * esz          # fwd: my ring block; bwd: every token
+        skv = B * S * Hkvl * D * esz
+        so = B * rows * H * D * esz
+        sstat = B * Hl * S * 4
+        sdkv = B * rows * Hkv * D * 4
         self.off_q = 0
         self.off_k = _align(self.off_q + sq)
         self.off_v = _align(self.off_k + skv)
-        self.off_o = _align(self.off_v + skv)                 # out (fwd) / dq (bwd)
-        self.off_do = _align(self.off_o + so)                  # dO stage (bwd)
+        self.off_o = _align(self.off_v + skv)                  # out (fwd) / dq (bwd)
+        self.off_lse_own = _align(self.off_o + so)              # (B, H, rows) fp32 LSE of my tokens (written by compute ranks)
+        self.off_do = _align(self.off_lse_own + B * H * rows * 4)
         self.off_delta = _align(self.off_do + (sq if self.with_bwd else 0))
-        self.off_dk = _align(self.off_delta + (sdelta if self.with_bwd else 0))
-        self.off_dv = _align(self.off_dk + sdkv)
-        total = _align(self.off_dv + sdkv) + _ALIGN
+        self.off_lse2 = _align(self.off_delta + (sstat if self.with_bwd else 0))
+        self.off_dk = _align(self.off_lse2 + (sstat if self.with_bwd else 0))
+        self.off_dv = _align(self.off_dk + (sdkv if self.with_bwd else 0))
+        total = _align(self.off_dv + (sdkv if self.with_bwd else 0)) + _ALIGN
         if self.slab is None or self.slab.nbytes < total:
             if self.slab is not None:
                 torch.cuda.synchronize(self.device)
@@ -153,7 +156,7 @@ class FusedUSPEngine:
             out_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
         lse = torch.empty((B, Hl, Sr), dtype=torch.float32, device=q.device)
 
-        qsegs, n_my_tiles = self._q_segments(variant, rows, push_q, self.off_o)
+        qsegs, n_my_tiles = self._q_segments(variant, rows, push_q, self.off_o, self.off_lse_own if push_q else None)
         ksegs = self._k_segments(variant, rows)
         qstride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
@@ -168,8 +171,12 @@ class FusedUSPEngine:
                   [P, U, R, u, r, rows, self.n_comm],
                   [self.off_q, self.off_k, self.off_v, Sr, P * rows],
                   slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
-        out = out_local.clone() if push_q else out_local   # the symmetric out buffer is reused next call
-        return out, lse
+        if push_q:   # the symmetric buffers are reused by the next call
+            out = out_local.clone()
+            lse_own = slab.tensor(self.off_lse_own, (B, H, rows), torch.float32).clone()
+        else:
+            out, lse_own = out_local, lse            # U == 1: (B, Hl, Sr) is already (B, H, rows)
+        return out, lse, lse_own
 
     # ------------------------------------------------------------------------------ segment builders
     def _alibi(self, p, Hl):
@@ -178,7 +185,7 @@ class FusedUSPEngine:
             return None
         return alibi.to(device=self.device, dtype=torch.float32)[..., self.u * Hl:(self.u + 1) * Hl].contiguous()
 
-    def _q_segments(self, variant, rows, pushed: bool, off_out: int):
+    def _q_segments(self, variant, rows, pushed: bool, off_out: int, off_lse=None):
         """Rows of my gathered Q (ring rank r) split by source shard -> kernel q segments
         [row0, nrows, pos0, flag, o_row0, o_base, o_sig, group]; also the number of 128-row tiles over MY rows."""
         U, R, u, r = self.U, self.R, self.u, self.r
@@ -193,7 +200,10 @@ class FusedUSPEngine:
                     flag = SIG_Q + su
                 else:
                     o_base, o_sig, flag = 0, 0, -1
-                segs.append([row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0])
+                seg = [row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0]
+                if off_lse is not None:
+                    seg.append(self.slab.peer_ptrs[owner] + off_lse)
+                segs.append(seg)
                 if su == u:
                     n_my_tiles += (s.count + 127) // 128
         segs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
@@ -213,9 +223,80 @@ class FusedUSPEngine:
         return segs
 
     # ------------------------------------------------------------------------------ backward
-    def backward(self, dout, q, k, v, out, lse, variant: str, p: AttnParams):
-        """Fused backward: dQ pass (with the push CTAs for q, dO, k, v, delta) scatters dQ tiles to the token
-        owners; dK/dV pass reduces its partial tiles into the owners' fp32 accumulators with red.add over NVLink."""
+    def backward(self, dout, q, k, v, out, lse, lse_own, variant: str, p: AttnParams):
+        """Owner-computes backward (default whenever ``Hkv % U == 0``).
+
+        dQ pass kernel: push CTAs send q, dO (+ delta, lse2) head-slices to EVERY sp-rank and k, v likewise; compute
+        CTAs produce dQ for my ring block's queries against all K/V and scatter dQ tiles to the token owners.
+        dK/dV pass kernel: stationary = the K/V rows of MY ring block, streamed = every rank's Q/dO as it arrived, so
+        dK/dV come out complete -- no cross-rank reduction, no fp32 traffic (the reference circulates fp32 dK/dV
+        partials around the ring for R hops, ``ring_flash_attn.py:141-145``) -- and are scattered to the token owners
+        in 16-bit like dQ."""
+        U = self.U
+        if k.shape[2] % U:
+            return self.backward_reduce(dout, q, k, v, out, lse, variant, p)
+        C = native.ext()
+        R, u, r, P = self.R, self.u, self.r, self.P
+        B, rows, H, D = q.shape
+        Hkv = k.shape[2]
+        esz = q.element_size()
+        Hl, Hkvl = H // U, Hkv // U
+        q, k, v, dout = (_dense_heads(t) for t in (q, k, v, dout))
+        self._ensure(B, rows, H, Hkv, D, esz)
+        slab = self.slab
+        Sr, S = U * rows, P * rows
+        delta_local = native.attn_delta(out, dout)                                   # (B, H, rows)
+        lse2_local = torch.where(torch.isinf(lse_own), torch.full_like(lse_own, float("inf")),
+                                 lse_own * 1.4426950408889634).contiguous()
+        q_all = slab.tensor(self.off_q, (B, S, Hl, D), q.dtype)
+        do_all = slab.tensor(self.off_do, (B, S, Hl, D), q.dtype)
+        kst = slab.tensor(self.off_k, (B, S, Hkvl, D), q.dtype)
+        vst = slab.tensor(self.off_v, (B, S, Hkvl, D), q.dtype)
+        delta_all = slab.tensor(self.off_delta, (B, Hl, S), torch.float32)
+        lse2_all = slab.tensor(self.off_lse2, (B, Hl, S), torch.float32)
+        dq_own = slab.tensor(self.off_o, (B, rows, H, D), q.dtype)
+        dk_own = slab.tensor(self.off_dk, (B, rows, Hkv, D), q.dtype)
+        dv_own = slab.tensor(self.off_dv, (B, rows, Hkv, D), q.dtype)
+        self.epoch += 1
+        fe = self.epoch * self.n_comm
+        stride = R if canonical_variant(variant) == "stripe" else 1
+        wl, wr = native.window_bounds(p)
+        alibi = self._alibi(p, Hl)
+        # every token shard of the mesh as a segment list over the (B, S, ...) all-rank staging layout
+        all_segs = []                     # (src, row0, nrows, pos0)
+        for sr in [(r - i) % R for i in range(R)]:
+            pos = ring_positions(variant, sr, R, Sr)
+            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
+            for su in us:
+                for sg, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
+                    all_segs.append((sr * U + su, sr * Sr + row0, sg.count, sg.start))
+        mine = [t for t in all_segs if t[0] // U == r]            # my ring block (queries I own after the Ulysses gather)
+        tiles_of_me = sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == self.me)
+        ksegs = [[row0, n, pos0, SIG_KV + src, 0] for (src, row0, n, pos0) in all_segs]
+        # ---- pass 1: dQ of my ring block's queries (stationary) against all K/V (streamed)
+        xq = [[row0, n, pos0, 0, row0 - src * rows, SIG_QA + src, slab.peer_ptrs[src] + self.off_o, 0,
+               self.sig.peer_ptrs[src] + 4 * SIG_ODONE] for (src, row0, n, pos0) in sorted(mine, key=lambda t: -t[3])]
+        self.o_total += U * B * Hl * tiles_of_me * 2
+        C.usp_bwd_pass(False, q_all, do_all, kst, vst, xq, ksegs, stride, stride, lse2_all, delta_all, dq_own, None, 0,
+                       u * Hl, float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe,
+                       [P, U, R, u, r, rows, self.n_comm], [q, dout], [self.off_q, self.off_do], [k, v],
+                       [self.off_k, self.off_v], [delta_local, lse2_local], [self.off_delta, self.off_lse2], True, Sr, S,
+                       slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
+        # ---- pass 2: dK/dV of my ring block's keys (stationary) against EVERY rank's queries (streamed)
+        xk = [[row0, n, pos0, 0, row0 - src * rows, SIG_KV + src, slab.peer_ptrs[src] + self.off_dk,
+               slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0) in mine]
+        yq = [[row0, n, pos0, SIG_QA + src, 0] for (src, row0, n, pos0) in all_segs]
+        self.dkv_total += U * B * Hkvl * tiles_of_me * 2
+        C.usp_bwd_pass(True, kst, vst, q_all, do_all, xk, yq, stride, stride, lse2_all, delta_all, dk_own, dv_own, 0,
+                       u * Hkvl, float(p.softmax_scale), wr, wl, float(p.softcap), alibi, self.sig.ptr, fe, [], [], [], [],
+                       [], [], [], False, Sr, S, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
+        C.symm_wait(self.sig.ptr + 4 * SIG_DKV, self.dkv_total & 0xFFFFFFFF)
+        return dq_own.clone(), dk_own.clone(), dv_own.clone()
+
+    def backward_reduce(self, dout, q, k, v, out, lse, variant: str, p: AttnParams):
+        """Reduction backward (used when kv heads are replicated across Ulysses ranks, ``Hkv < U``): every compute rank
+        forms partial dK/dV for all K/V rows it holds and reduces them into the owners' fp32 accumulators with
+        ``red.global.add.v4.f32`` over NVLink."""
         C = native.ext()
         U, R, u, r, P = self.U, self.R, self.u, self.r, self.P
         B, rows, H, D = q.shape
@@ -261,8 +342,8 @@ class FusedUSPEngine:
         ql, qo = ([q, dout], [self.off_q, self.off_do]) if pushed else ([], [])
         C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,
                        float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe, mesh, ql, qo, [k, v],
-                       [self.off_k, self.off_v], delta_local if pushed else None, self.off_delta, Sr, P * rows,
-                       slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
+                       [self.off_k, self.off_v], [delta_local] if pushed else [], [self.off_delta] if pushed else [],
+                       False, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
         # ---- pass 2: dK/dV for every K/V row I hold, reduced into the owners' accumulators
         h0 = u * Hkvl if Hkv >= U else (u * Hkv) // U
         xk, n_my_kv_tiles = [], 0
@@ -277,7 +358,7 @@ class FusedUSPEngine:
         self.dkv_total += P * B * Hkvl * n_my_kv_tiles * 2
         C.usp_bwd_pass(True, kst, vst, qst, dost, xk, yq, stride, stride, lse2, delta_c, dk_acc, dv_acc, 3, h0,
                        float(p.softmax_scale), wr, wl, float(p.softcap), alibi, self.sig.ptr, fe, [], [], [], [], [],
-                       None, 0, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
+                       [], [], False, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
         C.symm_wait(self.sig.ptr + 4 * SIG_DKV, self.dkv_total & 0xFFFFFFFF)
         dq = dq_local.clone() if pushed else dq_local
         return dq, dk_acc.to(k.dtype), dv_acc.to(v.dtype)
@@ -315,8 +396,8 @@ _SelfGroup = _SelfGroupType()
 class _FusedAttnFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams):
-        out, lse = eng.forward(q, k, v, variant, p)
-        ctx.save_for_backward(q, k, v, out, lse)
+        out, lse, lse_own = eng.forward(q, k, v, variant, p)
+        ctx.save_for_backward(q, k, v, out, lse, lse_own)
         ctx.eng, ctx.variant, ctx.p = eng, variant, p
         return out
 
@@ -326,10 +407,10 @@ class _FusedAttnFunc(torch.autograd.Function):
         from ..globals import PROCESS_GROUP
         from .all_to_all import all_to_all_4D
         from .ring_attention import ring_attn_backward
-        q, k, v, out, lse = ctx.saved_tensors
+        q, k, v, out, lse, lse_own = ctx.saved_tensors
         eng, p = ctx.eng, ctx.p
         if eng.with_bwd:
-            dq, dk, dv = eng.backward(dout, q, k, v, out, lse, ctx.variant, p)
+            dq, dk, dv = eng.backward(dout, q, k, v, out, lse, lse_own, ctx.variant, p)
             return dq, dk, dv, None, None, None
         ug, rg = eng.ulysses_pg, eng.ring_pg
         if eng.U > 1 and k.shape[2] % eng.U:
