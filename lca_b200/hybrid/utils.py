@@ -8,7 +8,8 @@ Unlike the reference, every key is usable with packed QKV.
 from ..parallel.ring_attention import (ring_flash_attn_func, ring_flash_attn_qkvpacked_func,
                                        stripe_flash_attn_func, stripe_flash_attn_qkvpacked_func,
                                        zigzag_ring_flash_attn_func, zigzag_ring_flash_attn_qkvpacked_func)
-from ..ring import ring_flashinfer_attn_func, ring_flashinfer_attn_qkvpacked_func, ring_pytorch_attn_func
+from ..ring import (ring_flashinfer_attn_func, ring_flashinfer_attn_qkvpacked_func, ring_npu_flash_attn_func,
+                    ring_pytorch_attn_func)
 
 RING_IMPL_DICT = {
     "basic": ring_flash_attn_func,
@@ -17,6 +18,7 @@ RING_IMPL_DICT = {
     "stripe": stripe_flash_attn_func,
     "basic_pytorch": ring_pytorch_attn_func,
     "basic_flashinfer": ring_flashinfer_attn_func,
+    "basic_npu": ring_npu_flash_attn_func,       # raises: Ascend-only in the reference
 }
 
 RING_IMPL_QKVPACKED_DICT = {

@@ -21,8 +21,10 @@ from enum import Enum
 
 import torch
 
-from .attention import (flash_attn_backward, flash_attn_forward, flash_attn_func,
-                        pytorch_attn_backward, pytorch_attn_forward, pytorch_attn_func)
+from .attention import (flash_attn3_func_backward, flash_attn3_func_forward, flash_attn_backward,
+                        flash_attn_forward, flash_attn_forward_aiter, flash_attn_func, flashinfer_attn_backbward,
+                        flashinfer_attn_backward, flashinfer_attn_forward, npu_fused_attn_backward,
+                        npu_fused_attn_forward, pytorch_attn_backward, pytorch_attn_forward, pytorch_attn_func)
 
 
 class AttnType(Enum):
@@ -73,4 +75,6 @@ def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_pro
 
 
 __all__ = ["AttnType", "select_flash_attn_impl", "flash_attn_forward", "flash_attn_backward", "flash_attn_func",
-           "pytorch_attn_forward", "pytorch_attn_backward", "pytorch_attn_func"]
+           "pytorch_attn_forward", "pytorch_attn_backward", "pytorch_attn_func", "flash_attn3_func_forward",
+           "flash_attn3_func_backward", "flashinfer_attn_forward", "flashinfer_attn_backbward", "flashinfer_attn_backward",
+           "flash_attn_forward_aiter", "npu_fused_attn_forward", "npu_fused_attn_backward"]

@@ -97,3 +97,42 @@ def flash_attn_func(q, k, v, *a, **kw):
 
 def pytorch_attn_func(q, k, v, *a, **kw):
     return _func("torch", q, k, v, *a, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Names of the reference's other per-library wrappers (``kernels/attention.py:253-457``).  On B200 the
+# FA3 / flashinfer entry points run the native tcgen05 engine; the ROCm / Ascend ones raise.
+# ------------------------------------------------------------------------------------------------
+def flash_attn3_func_forward(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                             alibi_slopes=None, return_softmax=False):
+    """Unlike the reference's FA3 wrapper (hard-codes ``causal=False`` and ``softcap=0``, ``:283-286``) every
+    argument is honoured."""
+    return _fwd(None, q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, return_softmax)
+
+
+def flash_attn3_func_backward(dout, q, k, v, out, softmax_lse, *a, **kw):
+    return _bwd(None, dout, q, k, v, out, softmax_lse, *a, **kw)
+
+
+def flashinfer_attn_forward(q, k, v, *a, **kw):
+    """Returns a natural-log LSE directly (the reference converts flashinfer's base-2 LSE, ``:393``)."""
+    return _fwd(None, q, k, v, *a, **kw)
+
+
+def flashinfer_attn_backbward(dout, q, k, v, out, softmax_lse, *a, **kw):   # (sic) reference spelling
+    return _bwd(None, dout, q, k, v, out, softmax_lse, *a, **kw)
+
+
+flashinfer_attn_backward = flashinfer_attn_backbward
+
+
+def _foreign(name, hw):
+    def fn(*a, **kw):
+        raise RuntimeError(f"{name} targets {hw}; not available in the B200 build (use flash_attn_forward/backward)")
+    fn.__name__ = name
+    return fn
+
+
+flash_attn_forward_aiter = _foreign("flash_attn_forward_aiter", "AMD ROCm (aiter)")
+npu_fused_attn_forward = _foreign("npu_fused_attn_forward", "Ascend NPU")
+npu_fused_attn_backward = _foreign("npu_fused_attn_backward", "Ascend NPU")

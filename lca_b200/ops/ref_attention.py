@@ -203,3 +203,15 @@ def attention_ref(
     if not upcast:
         q, k, v = (t.to(torch.float32).to(t.dtype) for t in (q, k, v))
     return attn_block_fwd_ref(q, k, v, q_pos, k_pos, softmax_scale, causal, window_size, softcap, alibi_slopes)
+
+
+def construct_local_mask(seqlen_q, seqlen_k, window_size=(-1, -1), query_padding_mask=None, key_padding_mask=None,
+                         device=None):
+    """Boolean (Sq, Sk) mask, True = masked, for a sliding window with bottom-right aligned diagonal (role of
+    ``test/test_utils.py:construct_local_mask``), expressed with the same position algebra as the kernels."""
+    q_pos = torch.arange(seqlen_q, device=device) + (seqlen_k - seqlen_q)
+    k_pos = torch.arange(seqlen_k, device=device)
+    mask, _ = _bias_and_mask(q_pos, k_pos, False, window_size, None, 1, device)
+    if mask is None:
+        mask = torch.zeros(seqlen_q, seqlen_k, dtype=torch.bool, device=device)
+    return mask

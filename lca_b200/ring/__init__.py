@@ -14,7 +14,7 @@ from ..parallel.ring_varlen import (ring_flash_attn_varlen_func, ring_flash_attn
                                     ring_flash_attn_varlen_qkvpacked_func, zigzag_ring_flash_attn_varlen_func,
                                     zigzag_ring_flash_attn_varlen_kvpacked_func,
                                     zigzag_ring_flash_attn_varlen_qkvpacked_func)
-from .utils import flatten_varlen_lse, unflatten_varlen_lse, update_out_and_lse
+from .utils import flatten_varlen_lse, unflatten_varlen_lse, update_npu_out, update_out_and_lse
 
 
 def ring_pytorch_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),

@@ -10,7 +10,7 @@ from ..ops import native
 from ..ops.attention import merge_out_lse_
 from ..parallel.ring_comm import RingComm
 
-__all__ = ["update_out_and_lse", "RingComm", "flatten_varlen_lse", "unflatten_varlen_lse"]
+__all__ = ["update_out_and_lse", "update_npu_out", "RingComm", "flatten_varlen_lse", "unflatten_varlen_lse"]
 
 
 def update_out_and_lse(out: Optional[torch.Tensor], lse: Optional[torch.Tensor], block_out: torch.Tensor,
@@ -52,3 +52,22 @@ def unflatten_varlen_lse(lse: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen
         s, e = int(cu_seqlens[i]), int(cu_seqlens[i + 1])
         out[i, :, : e - s] = lse[:, s:e]
     return out
+
+
+def update_npu_out(cur_attn_out, cur_softmax_max, cur_softmax_sum, prev_attn_out, prev_softmax_max, prev_softmax_sum,
+                   layout="BSND"):
+    """Merge two partial results given as ``(out, row_max, row_sum)`` triples -- the statistic format of fused
+    attention ops that return max/sum instead of an LSE (reference: ``ring/utils.py:54-93``, written for Ascend's
+    ``npu_fusion_attention``).  ``out`` is ``(B, S, N, D)``; ``max``/``sum`` are ``(B, N, S, k)`` with the value
+    replicated along the last axis.  Device-agnostic; equivalent to the LSE merge with ``lse = max + log(sum)``."""
+    assert layout == "BSND", "only the BSND layout is supported"
+    if prev_attn_out is None:
+        return cur_attn_out, cur_softmax_max, cur_softmax_sum
+    new_max = torch.maximum(prev_softmax_max, cur_softmax_max)
+    prev_scaled = prev_softmax_sum * torch.exp(prev_softmax_max - new_max)
+    cur_scaled = cur_softmax_sum * torch.exp(cur_softmax_max - new_max)
+    new_sum = prev_scaled + cur_scaled
+    w_prev = (prev_scaled / new_sum)[..., 0].transpose(1, 2).unsqueeze(-1)      # (B, S, N, 1)
+    w_cur = (cur_scaled / new_sum)[..., 0].transpose(1, 2).unsqueeze(-1)
+    out = (prev_attn_out.to(torch.float32) * w_prev + cur_attn_out.to(torch.float32) * w_cur).to(prev_attn_out.dtype)
+    return out, new_max, new_sum

@@ -112,3 +112,51 @@ def test_groups_block_diagonal():
     o0, _ = attention_ref(q[:, :4], k[:, :4], v[:, :4], causal=True)
     o1, _ = attention_ref(q[:, 4:], k[:, 4:], v[:, 4:], causal=True)
     torch.testing.assert_close(out, torch.cat([o0, o1], 1), atol=1e-5, rtol=1e-5)
+
+
+def test_triple_merge_matches_lse_merge():
+    """update_npu_out((out,max,sum) triples) == LSE merge (C9 parity)."""
+    from lca_b200.ring import update_npu_out
+    torch.manual_seed(0)
+    B, S, N, D = 2, 5, 3, 4
+    s1, s2 = torch.randn(B, N, S, 7), torch.randn(B, N, S, 6)
+    v1, v2 = torch.randn(B, N, 7, D), torch.randn(B, N, 6, D)
+    def part(s, v):
+        m = s.max(-1, keepdim=True).values
+        e = torch.exp(s - m)
+        l = e.sum(-1, keepdim=True)
+        return (e / l @ v).transpose(1, 2), m.expand(-1, -1, -1, 8), l.expand(-1, -1, -1, 8)
+    o1, m1, l1 = part(s1, v1)
+    o2, m2, l2 = part(s2, v2)
+    out, _, _ = update_npu_out(o2, m2, l2, o1, m1, l1)
+    ref = (torch.softmax(torch.cat([s1, s2], -1), -1) @ torch.cat([v1, v2], 2)).transpose(1, 2)
+    torch.testing.assert_close(out, ref, atol=1e-5, rtol=1e-5)
+
+
+def test_api_surface_matches_reference_names():
+    import lca_b200 as y
+    for name in ["LongContextAttention", "LongContextAttentionQKVPacked", "AsyncLongContextAttention", "UlyssesAttention",
+                 "set_seq_parallel_pg", "EXTRACT_FUNC_DICT", "RING_IMPL_QKVPACKED_DICT", "ring_flash_attn_func",
+                 "ring_flash_attn_kvpacked_func", "ring_flash_attn_qkvpacked_func", "zigzag_ring_flash_attn_func",
+                 "zigzag_ring_flash_attn_kvpacked_func", "zigzag_ring_flash_attn_qkvpacked_func", "stripe_flash_attn_func",
+                 "stripe_flash_attn_kvpacked_func", "stripe_flash_attn_qkvpacked_func", "ring_flash_attn_varlen_func",
+                 "ring_flash_attn_varlen_kvpacked_func", "ring_flash_attn_varlen_qkvpacked_func",
+                 "zigzag_ring_flash_attn_varlen_func", "zigzag_ring_flash_attn_varlen_qkvpacked_func",
+                 "ring_pytorch_attn_func", "ring_flashinfer_attn_func", "ring_flashinfer_attn_kvpacked_func",
+                 "ring_flashinfer_attn_qkvpacked_func", "ring_npu_flash_attn_func", "basic_extract_local",
+                 "stripe_extract_local", "zigzag_extract_local", "__version__"]:
+        assert hasattr(y, name), name
+    from lca_b200.kernels import AttnType, select_flash_attn_impl
+    assert {m.name for m in AttnType} >= {"AITER", "FA", "FA3", "FLASHINFER", "TORCH_MATH", "TORCH_FLASH", "TORCH_EFFICIENT",
+                                          "TORCH_CUDNN", "SAGE_AUTO", "SAGE_FP16", "SAGE_FP16_TRITON", "SAGE_FP8",
+                                          "SAGE_FP8_SM90", "SPARSE_SAGE", "NPU"}
+    assert AttnType.from_string("torch") is AttnType.TORCH
+    for stage in ("fwd-only", "bwd-only", "fwd-bwd"):
+        assert callable(select_flash_attn_impl(AttnType.FA, stage))
+        assert callable(select_flash_attn_impl(AttnType.TORCH_MATH, stage))
+    import pytest
+    with pytest.raises(ValueError):
+        select_flash_attn_impl(AttnType.NPU)
+    from lca_b200.comm import SeqAllToAll4D, SeqAllToAll5D, all_to_all_4D, all_to_all_5D   # noqa: F401
+    from lca_b200.ring.utils import RingComm, update_out_and_lse, flatten_varlen_lse, unflatten_varlen_lse  # noqa: F401
+    from lca_b200.globals import PROCESS_GROUP, HAS_FLASH_ATTN, HAS_FLASH_ATTN_HOPPER, HAS_FLASHINFER, HAS_NPU  # noqa: F401
