@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -169,6 +170,10 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   TORCH_CHECK(lse.size(0) == B && lse.size(1) == H && lse.size(2) >= q.size(1), "lse shape");
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
+  {
+    static int poly = [] { const char* e = std::getenv("LCA_B200_POLY_EVERY"); return e ? std::atoi(e) : 6; }();
+    p.poly_every = poly;
+  }
   p.lse_own_sb = out.size(2) * out.size(1);      // owners keep (B, H_total, rows) next to their (B, rows, H_total, D) output
   p.lse_own_sh = out.size(1);
 }

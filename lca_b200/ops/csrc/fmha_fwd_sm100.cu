@@ -144,7 +144,8 @@ struct Bars {
 
 }  // namespace
 
-template <int kD, bool kBf16>
+// kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
+template <int kD, bool kBf16, int kPolyEvery>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
@@ -417,12 +418,31 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         const float sub = (m == -INFINITY) ? 0.f : m;
         // ---- P = exp2(x*mul - m), row sum, pack, store over S
         float rs = 0.f;
+        if (general) {
 #pragma unroll
-        for (int c = 0; c < 128; c += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
-          const float p1 = ex2(fmaf(__uint_as_float(v[c + 1]), mul, -sub));
-          rs += p0 + p1;
-          v[c >> 1] = pack2<kBf16>(p0, p1);
+          for (int c = 0; c < 128; c += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
+            const float p1 = ex2(fmaf(__uint_as_float(v[c + 1]), mul, -sub));
+            rs += p0 + p1;
+            v[c >> 1] = pack2<kBf16>(p0, p1);
+          }
+        } else {
+          // unmasked tiles (the bulk of the work): every kPolyEvery-th pair takes the FMA-pipe exp2
+#pragma unroll
+          for (int c = 0; c < 128; c += 2) {
+            const float x0 = fmaf(__uint_as_float(v[c]), mul, -sub);
+            const float x1 = fmaf(__uint_as_float(v[c + 1]), mul, -sub);
+            float p0, p1;
+            if (kPolyEvery > 0 && ((c >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0) {
+              p0 = ex2_poly(x0);
+              p1 = ex2_poly(x1);
+            } else {
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            rs += p0 + p1;
+            v[c >> 1] = pack2<kBf16>(p0, p1);
+          }
         }
         l += rs;
         tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -515,10 +535,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16>
+template <int kD, bool kBf16, int kPoly>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -533,9 +553,19 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
   return cudaGetLastError();
 }
 
+template <int kD, bool kBf16>
+static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  switch (p.poly_every) {
+    case 0: return launch_impl<kD, kBf16, 0>(p, num_sms, stream);
+    case 3: return launch_impl<kD, kBf16, 3>(p, num_sms, stream);
+    case 6: return launch_impl<kD, kBf16, 6>(p, num_sms, stream);
+    default: return launch_impl<kD, kBf16, 4>(p, num_sms, stream);
+  }
+}
+
 cudaError_t launch_fmha_fwd(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream) {
-  if (head_dim == 128) return bf16 ? launch_impl<128, true>(p, num_sms, stream) : launch_impl<128, false>(p, num_sms, stream);
-  if (head_dim == 64) return bf16 ? launch_impl<64, true>(p, num_sms, stream) : launch_impl<64, false>(p, num_sms, stream);
+  if (head_dim == 128) return bf16 ? launch_poly<128, true>(p, num_sms, stream) : launch_poly<128, false>(p, num_sms, stream);
+  if (head_dim == 64) return bf16 ? launch_poly<64, true>(p, num_sms, stream) : launch_poly<64, false>(p, num_sms, stream);
   return cudaErrorInvalidValue;
 }
 

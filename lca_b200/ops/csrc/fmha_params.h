@@ -97,6 +97,7 @@ struct FwdParams {
   int64_t lse_own_sb, lse_own_sh;     // strides of the owners' LSE buffers (QSegD::lse_base), indexed like the output
   const uint32_t* flags;              // arrival flags written by peers (fused paths)
   uint32_t flag_epoch;
+  int poly_every;                     // exp2 offload ratio: 1 of every N element pairs on the FMA pipe (0, 3, 4, 6)
   CommParams comm;
 };
 

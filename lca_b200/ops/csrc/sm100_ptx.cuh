@@ -250,6 +250,16 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA/ALU pipes (Cody-Waite range reduction + cubic minimax, max rel. error 1.0e-4, far below bf16
+// rounding).  Used for a fraction of the softmax elements so the MUFU pipe (16 ex2/clk/SM) is no longer the
+// only exp engine.  Requires a finite argument; very negative arguments are clamped (result ~1e-38).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;               // 1.5 * 2^23: rounds x to the nearest integer in the low mantissa bits
+  const float f = x - (t - 12582912.f);         // f in [-0.5, 0.5]
+  const float p = fmaf(fmaf(fmaf(0.0550089f, f, 0.24221097f), f, 0.69328293f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
