@@ -235,11 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       // =========================================================== producer (whole warp: lane 0 drives TMA,
       // all lanes fetch the per-column lse2/delta of streamed query tiles in the dKV pass)
       uint32_t xc = 0, yc = 0;
+      int x_ok = -1, y_ok = -1;     // last arrival flags already acquired (a flag only ever needs one acquire per launch)
       for (int round = 0;; ++round) {
         Work wk;
         if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
         if (lane == 0) {
-          wait_arrival(p.flags, p.flag_epoch, p.xseg[wk.xseg].flag);
+          const int xf = p.xseg[wk.xseg].flag;
+          if (xf >= 0 && xf != x_ok) { wait_arrival(p.flags, p.flag_epoch, xf); x_ok = xf; }
           mbar_wait(x_empty, (xc & 1) ^ 1);
           mbar_arrive_expect_tx(x_full, 2 * C::XTILE_BYTES);
 #pragma unroll
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           const uint32_t st = yc % C::STAGES;
           const uint32_t par = (yc / C::STAGES) & 1;
           if (lane == 0) {
-            wait_arrival(p.flags, p.flag_epoch, it.flag);
+            if (it.flag >= 0 && it.flag != y_ok) { wait_arrival(p.flags, p.flag_epoch, it.flag); y_ok = it.flag; }
             mbar_wait(y_empty + 8 * st, par ^ 1);
             mbar_arrive_expect_tx(y_full + 8 * st, 2 * C::YTILE_BYTES);
 #pragma unroll

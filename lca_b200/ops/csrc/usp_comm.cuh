@@ -14,7 +14,7 @@ namespace lca {
 
 // Spin-wait watchdog: a peer that never arrives (crashed rank, mismatched call sequence) must not hang the
 // GPU forever -- after ~30 s of polling the kernel traps, which surfaces as a CUDA error on the host.
-constexpr unsigned long long kWatchdogPolls = 1ull << 28;
+constexpr unsigned long long kWatchdogPolls = 1ull << 24;   // ~1-2 us per poll
 
 static __device__ __noinline__ void spin_until_ge(const uint32_t* addr, uint32_t target, unsigned ns) {
   unsigned long long polls = 0;

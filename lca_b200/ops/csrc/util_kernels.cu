@@ -182,7 +182,7 @@ __global__ void wait_counter_kernel(const uint32_t* sig, uint32_t target) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sig) : "memory");
     if (static_cast<int32_t>(v - target) >= 0) break;
     __nanosleep(100);
-    if (++polls > (1ull << 28)) {      // ~30 s: a peer never delivered -> fail loudly instead of hanging the GPU
+    if (++polls > (1ull << 24)) {      // ~30 s: a peer never delivered -> fail loudly instead of hanging the GPU
       printf("[lca_b200] watchdog: counter %p stuck at %u, waiting for %u\n", sig, v, target);
       __trap();
     }
