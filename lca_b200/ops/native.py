@@ -33,7 +33,7 @@ def _load():
 
 LAUNCHES = 0     # number of in-tree CUDA kernels launched through this module (bench.py reports it)
 _KERNEL_FUNCS = {"fmha_fwd", "fmha_bwd_pass", "merge_out_lse", "finalize_out", "flatten_varlen_lse",
-                 "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd", "symm_barrier"}
+                 "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd_pass", "symm_wait"}
 
 
 class _CountingExt:
