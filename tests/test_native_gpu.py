@@ -247,3 +247,27 @@ def test_padded_head_dims(D):
     torch.testing.assert_close(out.float(), ref.float(), atol=2e-2, rtol=0)
     for a, b in ((q.grad, q2.grad), (k.grad, k2.grad), (v.grad, v2.grad)):
         assert (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-6) < 3e-2
+
+
+def test_varlen_groups_native_backward():
+    """Packed varlen batch (one attention group per sequence) through the native backward passes."""
+    native = _native()
+    from lca_b200.ops.attention import AttnParams
+    from lca_b200.kernels.attention import pytorch_attn_func
+    from lca_b200.parallel.layout import varlen_positions
+    lens = [300, 129, 1000, 64]
+    cu = [0]
+    for l in lens:
+        cu.append(cu[-1] + l)
+    q, k, v = _mk(1, cu[-1], cu[-1], 4, 2, 128)
+    do = torch.randn_like(q)
+    spec = varlen_positions("basic", 0, 1, cu)
+    p = AttnParams.make(q, None, True)
+    out, lse = native.fmha_fwd(q, k, v, spec, spec, p)
+    dq, dk, dv = native.fmha_bwd(do, q, k, v, out, lse, spec, spec, p)
+    for i in range(len(lens)):
+        sl = slice(cu[i], cu[i + 1])
+        q1, k1, v1 = (t[:, sl].detach().clone().requires_grad_() for t in (q, k, v))
+        pytorch_attn_func(q1, k1, v1, causal=True).backward(do[:, sl])
+        for a, b in ((dq[:, sl], q1.grad), (dk[:, sl], k1.grad), (dv[:, sl], v1.grad)):
+            assert (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-6) < 3e-2
