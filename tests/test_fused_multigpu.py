@@ -127,3 +127,12 @@ def test_collective_backend_2gpu(U, R, variant):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     run_distributed(_collective_worker, 2, U, R, variant, backend="nccl", timeout=90)
+
+
+@pytest.mark.parametrize("U,R,variant", [(2, 1, "basic"), (1, 2, "zigzag")])
+def test_fused_batch2_2gpu(U, R, variant):
+    """B = 2 through the fused path (staging batch strides, counters scale with B)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_distributed(_worker, 2, U, R, variant, dict(causal=True, _b1=False), 4, 2, 1024, 128, "hybrid", True,
+                    backend="nccl", timeout=90)
