@@ -53,6 +53,17 @@ class AttnType(Enum):
         raise ValueError(f"'{s}' is not a valid {cls.__name__}")
 
 
+def flash_attn_forward_fp8(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
+                           alibi_slopes=None, return_softmax=False):
+    """Uniform-contract forward on block-scaled e4m3 operands (quantised on the fly).  EXPERIMENTAL."""
+    from ..ops.attention import AttnParams
+    from ..ops.fp8 import attn_fp8_fwd
+    from ..parallel.layout import Seg
+    p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes)
+    Sq, Sk = q.shape[1], k.shape[1]
+    return attn_fp8_fwd(q, k, v, (Seg(max(Sk - Sq, 0), Sq, 1),), (Seg(0, Sk, 1),), p)
+
+
 _FOREIGN = {AttnType.AITER: "AMD ROCm (aiter)", AttnType.NPU: "Ascend NPU"}
 
 
@@ -67,6 +78,10 @@ def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_pro
     if stage not in ("fwd-only", "bwd-only", "fwd-bwd"):
         raise ValueError(f"Unknown stage: {stage}")
     torch_like = is_torch_type(impl_type)
+    if impl_type in (AttnType.SAGE_FP8, AttnType.SAGE_FP8_SM90) and stage == "fwd-only":
+        from ..ops import fp8
+        if fp8.enabled():            # experimental e4m3 block-scaled forward (forward-only, like the reference's SAGE_FP8)
+            return flash_attn_forward_fp8
     if stage == "fwd-only":
         return pytorch_attn_forward if torch_like else flash_attn_forward
     if stage == "bwd-only":

@@ -57,6 +57,26 @@ bool encode_tmap_4d(CUtensorMap* out, const void* base, int64_t D, int64_t H, in
   return true;
 }
 
+// 1-byte (e4m3) tensors: box (128 bytes, 1, 128 rows, 1)
+static void make_tmap_u8(CUtensorMap* m, const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.dim() == 4 && t.element_size() == 1 && t.stride(3) == 1, name, " must be a (B, S, H, D) 1-byte tensor");
+  const int64_t B = t.size(0), S = t.size(1), H = t.size(2), D = t.size(3);
+  int64_t sb = t.stride(0), ss = t.stride(1), sh = t.stride(2);
+  if (B == 1) sb = S * ss;
+  if (H == 1) sh = D;
+  EncodeTiledFn fn = get_encode_fn();
+  TORCH_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  TORCH_CHECK(reinterpret_cast<uintptr_t>(t.data_ptr()) % 16 == 0 && sh % 16 == 0 && ss % 16 == 0 && sb % 16 == 0, name,
+              ": 16-byte alignment");
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(sh), static_cast<cuuint64_t>(ss), static_cast<cuuint64_t>(sb)};
+  cuuint32_t box[4] = {128, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, t.data_ptr(), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, name, ": cuTensorMapEncodeTiled failed");
+}
+
 static void make_tmap(CUtensorMap* m, const at::Tensor& t, const char* name, int box_rows = 128) {
   TORCH_CHECK(t.dim() == 4, name, " must be (B, S, H, D)");
   TORCH_CHECK(t.stride(3) == 1, name, " last dim must be contiguous");
@@ -248,6 +268,87 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
   c.stage_q_rows = stage_q_rows; c.stage_kv_rows = stage_kv_rows;
   c.epoch = static_cast<unsigned int>(epoch);
   c.o_target = static_cast<unsigned int>(o_target);
+}
+
+// EXPERIMENTAL fp8 (e4m3) forward.  q8/k8/v8: (B,S,H|Hkv,128) uint8/float8 views, scales from quantize_e4m3.
+void fmha_fwd_fp8(const at::Tensor& q8, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& q_scale,
+                  const at::Tensor& k_scale, const at::Tensor& v_scale, const std::vector<std::vector<int64_t>>& qsegs,
+                  const std::vector<std::vector<int64_t>>& ksegs, int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out,
+                  at::Tensor& lse, double scale, int64_t wl, int64_t wr, double softcap,
+                  const c10::optional<at::Tensor>& alibi) {
+  TORCH_CHECK(q8.is_cuda() && q8.element_size() == 1 && k8.element_size() == 1 && v8.element_size() == 1, "fp8 operands");
+  const int64_t B = q8.size(0), H = q8.size(2), D = q8.size(3), Hkv = k8.size(2);
+  TORCH_CHECK(D == 128 && k8.size(3) == 128 && v8.size(3) == 128, "fp8 path: head_dim 128 only");
+  TORCH_CHECK(H % Hkv == 0 && v8.size(2) == Hkv && k8.size(0) == B && v8.size(1) == k8.size(1), "bad k/v shape");
+  TORCH_CHECK(out.scalar_type() == at::kBFloat16 && out.stride(3) == 1 && lse.scalar_type() == at::kFloat, "out bf16 / lse fp32");
+  for (const at::Tensor* t : {&q_scale, &k_scale, &v_scale}) TORCH_CHECK(t->scalar_type() == at::kFloat && t->is_contiguous(), "scales");
+  TORCH_CHECK(q_scale.dim() == 3 && q_scale.size(0) == B && q_scale.size(1) == H && q_scale.size(2) == (q8.size(1) + 127) / 128, "q_scale");
+  TORCH_CHECK(k_scale.dim() == 3 && k_scale.size(1) == Hkv && k_scale.size(2) == (k8.size(1) + 127) / 128, "k_scale");
+  TORCH_CHECK(v_scale.dim() == 2 && v_scale.size(0) == B && v_scale.size(1) == Hkv, "v_scale");
+  TORCH_CHECK(!qsegs.empty() && qsegs.size() <= kMaxSeg && !ksegs.empty() && ksegs.size() <= kMaxSeg, "segment count");
+  c10::cuda::CUDAGuard guard(q8.device());
+  FwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  make_tmap_u8(&p.tm_q, q8, "q8");
+  make_tmap_u8(&p.tm_k, k8, "k8");
+  make_tmap_u8(&p.tm_v, v8, "v8");
+  p.n_qseg = static_cast<int>(qsegs.size());
+  p.n_kseg = static_cast<int>(ksegs.size());
+  int64_t pairs = 0;
+  for (int i = 0; i < p.n_qseg; ++i) {
+    const auto& s = qsegs[i];
+    TORCH_CHECK(s.size() >= 8 && s[0] % 128 == 0 && s[0] + s[1] <= q8.size(1), "fp8 q segments must start on 128-row blocks");
+    p.qseg[i].row0 = static_cast<int>(s[0]); p.qseg[i].nrows = static_cast<int>(s[1]); p.qseg[i].pos0 = static_cast<int>(s[2]);
+    p.qseg[i].flag = -1; p.qseg[i].o_row0 = static_cast<int>(s[4]); p.qseg[i].o_base = out.data_ptr();
+    p.qseg[i].o_sig = nullptr; p.qseg[i].group = static_cast<int>(s[7]); p.qseg[i].lse_base = nullptr;
+    pairs += (s[1] + 255) / 256;
+  }
+  for (int i = 0; i < p.n_kseg; ++i) {
+    const auto& s = ksegs[i];
+    TORCH_CHECK(s.size() == 5 && s[0] % 128 == 0 && s[0] + s[1] <= k8.size(1), "fp8 k segments must start on 128-row blocks");
+    p.kseg[i].row0 = static_cast<int>(s[0]); p.kseg[i].nrows = static_cast<int>(s[1]); p.kseg[i].pos0 = static_cast<int>(s[2]);
+    p.kseg[i].flag = -1; p.kseg[i].group = static_cast<int>(s[4]);
+  }
+  p.q_pos_stride = static_cast<int>(q_pos_stride); p.k_pos_stride = static_cast<int>(k_pos_stride);
+  p.B = static_cast<int>(B); p.H = static_cast<int>(H); p.Hkv = static_cast<int>(Hkv);
+  p.total_work = static_cast<int>(pairs * B * H);
+  p.wl = static_cast<int>(wl); p.wr = static_cast<int>(wr);
+  p.scale = static_cast<float>(scale); p.scale_log2 = static_cast<float>(scale * 1.4426950408889634);
+  p.softcap = static_cast<float>(softcap);
+  if (alibi.has_value() && alibi->defined()) {
+    TORCH_CHECK(alibi->is_cuda() && alibi->scalar_type() == at::kFloat && alibi->is_contiguous(), "alibi");
+    p.alibi = alibi->data_ptr<float>();
+    p.alibi_bstride = alibi->dim() == 2 ? static_cast<int>(H) : 0;
+  }
+  p.o_sb = out.stride(0); p.o_ss = out.stride(1); p.o_sh = out.stride(2);
+  p.lse = lse.data_ptr<float>(); p.lse_sb = lse.stride(0); p.lse_sh = lse.stride(1);
+  p.poly_every = 6;
+  p.q_scale = q_scale.data_ptr<float>(); p.k_scale = k_scale.data_ptr<float>(); p.v_scale = v_scale.data_ptr<float>();
+  p.q_scale_sb = q_scale.stride(0); p.q_scale_sh = q_scale.stride(1);
+  p.k_scale_sb = k_scale.stride(0); p.k_scale_sh = k_scale.stride(1);
+  LCA_CUDA_OK(launch_fmha_fwd_fp8(p, 128, num_sms(), at::cuda::getCurrentCUDAStream()));
+}
+
+// bf16/fp16 (B,S,H,D) -> (e4m3 bytes (B,S,H,D), scale).  per_head: one scale per (b,h) [V]; else per 128-row block [Q, K].
+std::vector<at::Tensor> quantize_e4m3(const at::Tensor& x, bool per_head) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.stride(3) == 1 && (x.scalar_type() == at::kBFloat16 || x.scalar_type() == at::kHalf));
+  const int B = x.size(0), S = x.size(1), H = x.size(2), D = x.size(3);
+  TORCH_CHECK(D % 8 == 0 && x.stride(2) % 8 == 0 && x.stride(1) % 8 == 0, "alignment");
+  c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor y = at::empty({B, S, H, D}, x.options().dtype(at::kByte));
+  at::Tensor scale, ext;
+  const float* ext_p = nullptr;
+  const int nblk = (S + 127) / 128;
+  if (per_head) {
+    ext = (x.abs().amax({1, 3}).to(at::kFloat) / 448.0).clamp_min(1e-12).contiguous();     // (B, H)
+    ext_p = ext.data_ptr<float>();
+    scale = ext;
+  } else {
+    scale = at::empty({B, H, nblk}, x.options().dtype(at::kFloat));
+  }
+  LCA_CUDA_OK(launch_quant_e4m3(x.data_ptr(), dtype_code(x), y.data_ptr<uint8_t>(), per_head ? nullptr : scale.data_ptr<float>(),
+                                ext_p, B, S, H, D, x.stride(0), x.stride(1), x.stride(2), at::cuda::getCurrentCUDAStream()));
+  return {y, scale};
 }
 
 // Fused USP forward: the same kernel with `n_comm` communication CTAs that push this rank's q/k/v shards
@@ -524,6 +625,8 @@ std::vector<at::Tensor> attn_delta(const at::Tensor& out, const at::Tensor& dout
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "lca_b200 sm_100a kernels";
   m.def("fmha_fwd", &lca::fmha_fwd, "tcgen05 flash-attention forward (segments + global positions)");
+  m.def("fmha_fwd_fp8", &lca::fmha_fwd_fp8, "EXPERIMENTAL: e4m3 block-scaled forward (tcgen05 kind::f8f6f4)");
+  m.def("quantize_e4m3", &lca::quantize_e4m3, "bf16/fp16 -> e4m3 with per-128-row-block (or per-head) fp32 scales");
   m.def("usp_fwd", &lca::usp_fwd, "fused USP forward: NVLink push CTAs + tcgen05 attention CTAs in one kernel");
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");

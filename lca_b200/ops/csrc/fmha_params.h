@@ -99,6 +99,11 @@ struct FwdParams {
   uint32_t flag_epoch;
   int poly_every;                     // exp2 offload ratio: 1 of every N element pairs on the FMA pipe (0, 3, 4, 6)
   CommParams comm;
+  // fp8 path only (fmha_fwd_fp8_sm100.cu): block scales of the e4m3 operands
+  const float* q_scale;               // (B, H, ceil(Sq/128))
+  const float* k_scale;               // (B, Hkv, ceil(Sk/128))
+  const float* v_scale;               // (B, Hkv)
+  int64_t q_scale_sb, q_scale_sh, k_scale_sb, k_scale_sh;
 };
 
 // ---- backward -----------------------------------------------------------------------------------

@@ -11,6 +11,9 @@ namespace lca {
 // fmha_fwd_sm100.cu
 cudaError_t launch_fmha_fwd(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream);
 
+// fmha_fwd_fp8_sm100.cu (experimental)
+cudaError_t launch_fmha_fwd_fp8(const FwdParams& p, int head_dim, int num_sms, cudaStream_t stream);
+
 // fmha_bwd_sm100.cu
 cudaError_t launch_fmha_bwd(const BwdParams& p, int head_dim, bool bf16, bool is_dkv, int num_sms, cudaStream_t stream);
 
@@ -30,6 +33,8 @@ cudaError_t launch_delta(const void* out, const void* dout, int dtype, float* de
                          int64_t o_sb, int64_t o_ss, int64_t o_sh, int64_t do_sb, int64_t do_ss, int64_t do_sh,
                          cudaStream_t stream);
 
+cudaError_t launch_quant_e4m3(const void* x, int dtype, uint8_t* y, float* scale, const float* ext_scale, int B, int S, int H,
+                              int D, int64_t sb, int64_t ss, int64_t sh, cudaStream_t stream);
 cudaError_t launch_wait_counter(const uint32_t* sig, uint32_t target, cudaStream_t stream);
 
 // tensor-map helper (tma_host.cpp part of bindings): 4-D (D, H, S, B) 16-bit tensor, box (64,1,128,1), SWIZZLE_128B

@@ -189,6 +189,59 @@ __global__ void wait_counter_kernel(const uint32_t* sig, uint32_t target) {
   } while (true);
 }
 
+// bf16/fp16 (B,S,H,D) -> e4m3 (B,S,H,D) with one fp32 scale per (b, h, 128-row block) [or a caller-provided per-(b,h)
+// scale when ext_scale != nullptr].  scale = amax / 448 so that x / scale fills the e4m3 range.  grid (nblk, H, B).
+template <typename T>
+__global__ void quant_e4m3_kernel(const T* __restrict__ x, uint8_t* __restrict__ y, float* __restrict__ scale,
+                                  const float* __restrict__ ext_scale, int S, int H, int D, int64_t sb, int64_t ss,
+                                  int64_t sh, int nblk) {
+  const int blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int r0 = blk * 128;
+  const int nrows = min(128, S - r0);
+  const int vec_per_row = D / 8;
+  const int total = nrows * vec_per_row;
+  const T* base = x + b * sb + static_cast<int64_t>(r0) * ss + h * sh;
+  __shared__ float red[32];
+  float sc;
+  if (ext_scale != nullptr) {
+    sc = ext_scale[b * H + h];
+  } else {
+    float amax = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int r = i / vec_per_row, c = i - r * vec_per_row;
+      const uint4 v = *reinterpret_cast<const uint4*>(base + r * ss + c * 8);
+      const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) amax = fmaxf(amax, fabsf(to_f(e[k])));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float a = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
+      if (threadIdx.x == 0) red[0] = a;
+    }
+    __syncthreads();
+    sc = red[0] > 0.f ? red[0] / 448.f : 1.f;
+    if (threadIdx.x == 0) scale[(static_cast<int64_t>(b) * H + h) * nblk + blk] = sc;
+  }
+  const float inv = 1.f / sc;
+  uint8_t* ybase = y + ((static_cast<int64_t>(b) * S + r0) * H + h) * D;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / vec_per_row, c = i - r * vec_per_row;
+    const uint4 v = *reinterpret_cast<const uint4*>(base + r * ss + c * 8);
+    const T* e = reinterpret_cast<const T*>(&v);
+    uint16_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(o[k]) : "f"(to_f(e[2 * k + 1]) * inv), "f"(to_f(e[2 * k]) * inv));
+    *reinterpret_cast<uint2*>(ybase + static_cast<int64_t>(r) * H * D + c * 8) = *reinterpret_cast<uint2*>(o);
+  }
+}
+
 inline int grid_for(int64_t work_items, int threads) {
   int64_t g = (work_items + threads - 1) / threads;
   const int64_t cap = 148 * 16;
@@ -247,6 +300,18 @@ cudaError_t launch_permute_heads_in(const void* src, void* dst, int B, int S, in
   const int64_t BS = static_cast<int64_t>(B) * S;
   const int xv = x_bytes / 16;
   permute_kernel<false><<<grid_for(BS * G * xv, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), BS, G, xv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quant_e4m3(const void* x, int dtype, uint8_t* y, float* scale, const float* ext_scale, int B, int S, int H,
+                              int D, int64_t sb, int64_t ss, int64_t sh, cudaStream_t stream) {
+  if (D % 8) return cudaErrorInvalidValue;
+  const int nblk = (S + 127) / 128;
+  dim3 grid(nblk, H, B);
+  if (dtype == 1)
+    quant_e4m3_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), y, scale, ext_scale, S, H, D, sb, ss, sh, nblk);
+  else
+    quant_e4m3_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(x), y, scale, ext_scale, S, H, D, sb, ss, sh, nblk);
   return cudaGetLastError();
 }
 
