@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -99,6 +100,34 @@ static int num_sms() {
   static int n = 0;
   if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
   return n;
+}
+
+// ---- dynamic tile scheduler state (EXPERIMENTAL, LCA_B200_DYN_SCHED=1): one monotonic counter per device; the host
+// tracks its value at the start of each launch (every launch claims total_work + #compute-CTA indices).  Assumes the
+// launches of one device are issued in stream order (single compute stream).
+struct SchedState {
+  at::Tensor counter;
+  uint32_t base = 0;
+};
+static bool dyn_sched_enabled() {
+  static bool e = [] { const char* v = std::getenv("LCA_B200_DYN_SCHED"); return v && std::atoi(v) == 1; }();
+  return e;
+}
+template <typename P>
+static void attach_sched(P& p, const at::Tensor& like, int sms, int n_comm) {
+  if (!dyn_sched_enabled()) return;
+  static std::mutex mu;
+  static std::map<int, SchedState> states;
+  std::lock_guard<std::mutex> lock(mu);
+  SchedState& st = states[like.get_device()];
+  if (!st.counter.defined()) st.counter = at::zeros({1}, like.options().dtype(at::kInt));
+  p.sched_counter = reinterpret_cast<uint32_t*>(st.counter.data_ptr<int>());
+  p.sched_base = st.base;
+  p.dyn_sched = 1;
+  const int avail = sms - n_comm;
+  int gc = p.total_work < avail ? p.total_work : avail;
+  if (gc < 1) gc = 1;
+  st.base += static_cast<uint32_t>(p.total_work) + static_cast<uint32_t>(gc);
 }
 
 #define LCA_CUDA_OK(expr)                                                                   \
@@ -209,6 +238,7 @@ void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                   alibi, flags_ptr, flag_epoch);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  attach_sched(p, q, sms, 0);
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
                               at::cuda::getCurrentCUDAStream()));
 }
@@ -373,6 +403,7 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
   if (mesh.at(1) > 1) { ql.push_back(uq); qo.push_back(offs[0]); }
   fill_comm(p.comm, mesh, ql, qo, kvl, kvo, {}, {}, false, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
             o_target, uq.size(2), uk.size(2));
+  attach_sched(p, q, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }
@@ -483,6 +514,7 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
                   f32 ? (accumulate ? 2 : 1) : 0, scale, wl, wr, softcap, alibi);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  attach_sched(p, x0, sms, 0);
   LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, sms,
                               at::cuda::getCurrentCUDAStream()));
 }
@@ -513,6 +545,7 @@ void usp_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const
   if (!mesh.empty())
     fill_comm(p.comm, mesh, qlike, q_offs, kvlike, kv_offs, stats, stat_offs, q_to_all, stage_q_rows, stage_kv_rows,
               peer_slabs, peer_sigs, my_sig, epoch, o_target, H, Hkv);
+  attach_sched(p, x0, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }

@@ -175,7 +175,8 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 
 }  // namespace
 
-template <int kD, bool kBf16, bool kIsDKV>
+// kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
@@ -202,8 +203,42 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
   const uint32_t st_empty = a; a += 8 * C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::OFF_BAR + 480);
   float* stat = reinterpret_cast<float*>(smem_gen + C::OFF_STAT);
+  const uint32_t sc_full = smem + C::OFF_BAR + 400, sc_empty = smem + C::OFF_BAR + 416;   // dynamic scheduler ring
+  volatile int* sched_idx = reinterpret_cast<volatile int*>(smem_gen + C::OFF_BAR + 432);
+  auto producer_next = [&](int round) -> int {          // called by ALL lanes of the producer warp
+    if constexpr (kDyn) {
+      const uint32_t slot = round & 1, par = (round >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(sc_empty + 8 * slot, par ^ 1);
+        sched_idx[slot] = static_cast<int>(atomicAdd(p.sched_counter, 1u) - p.sched_base);
+        mbar_arrive(sc_full + 8 * slot);
+      }
+      __syncwarp();
+      return sched_idx[slot];
+    } else {
+      return sched_work(round, p.comm.n_comm);
+    }
+  };
+  auto consumer_next = [&](int round) -> int {
+    if constexpr (kDyn) {
+      const uint32_t slot = round & 1, par = (round >> 1) & 1;
+      mbar_wait(sc_full + 8 * slot, par);
+      const int w = sched_idx[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sc_empty + 8 * slot);
+      return w;
+    } else {
+      return sched_work(round, p.comm.n_comm);
+    }
+  };
 
   if (threadIdx.x == 0) {
+    if constexpr (kDyn) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(sc_full + 8 * s, 1);
+        mbar_init(sc_empty + 8 * s, 9);    // MMA warp + 8 element-wise warps
+      }
+    }
     mbar_init(x_full, 1);
     mbar_init(x_empty, 1);
     mbar_init(acc_full, 1);
@@ -238,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       int x_ok = -1, y_ok = -1;     // last arrival flags already acquired (a flag only ever needs one acquire per launch)
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+        if (!decode_work(p, producer_next(round), wk)) break;
         if (lane == 0) {
           const int xf = p.xseg[wk.xseg].flag;
           if (xf >= 0 && xf != x_ok) { wait_arrival(p.flags, p.flag_epoch, xf); x_ok = xf; }
@@ -325,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         };
         for (int round = 0;; ++round) {
           Work wk;
-          if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+          if (!decode_work(p, consumer_next(round), wk)) break;
           TileIter it;
           it.init(p, wk);
           mbar_wait(x_full, xc & 1);
@@ -392,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
-      if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+      if (!decode_work(p, consumer_next(round), wk)) break;
       const int xpos = wk.pos0 + row * p.x_pos_stride;
       const int xhi = wk.pos0 + (BX - 1) * p.x_pos_stride;
       const bool row_ok = row < wk.nrows;
@@ -563,10 +598,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -581,12 +616,16 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
   return cudaGetLastError();
 }
 
+template <int kD, bool kBf16>
+static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
+  if (p.dyn_sched)
+    return is_dkv ? launch_impl<kD, kBf16, true, true>(p, num_sms, stream) : launch_impl<kD, kBf16, false, true>(p, num_sms, stream);
+  return is_dkv ? launch_impl<kD, kBf16, true, false>(p, num_sms, stream) : launch_impl<kD, kBf16, false, false>(p, num_sms, stream);
+}
+
 cudaError_t launch_fmha_bwd(const BwdParams& p, int head_dim, bool bf16, bool is_dkv, int num_sms, cudaStream_t stream) {
-#define LCA_DISPATCH(D, BF)                                                                 \
-  return is_dkv ? launch_impl<D, BF, true>(p, num_sms, stream) : launch_impl<D, BF, false>(p, num_sms, stream)
-  if (head_dim == 128) { if (bf16) { LCA_DISPATCH(128, true); } else { LCA_DISPATCH(128, false); } }
-  if (head_dim == 64) { if (bf16) { LCA_DISPATCH(64, true); } else { LCA_DISPATCH(64, false); } }
-#undef LCA_DISPATCH
+  if (head_dim == 128) return bf16 ? launch_pass<128, true>(p, is_dkv, num_sms, stream) : launch_pass<128, false>(p, is_dkv, num_sms, stream);
+  if (head_dim == 64) return bf16 ? launch_pass<64, true>(p, is_dkv, num_sms, stream) : launch_pass<64, false>(p, is_dkv, num_sms, stream);
   return cudaErrorInvalidValue;
 }
 

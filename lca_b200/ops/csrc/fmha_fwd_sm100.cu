@@ -145,7 +145,9 @@ struct Bars {
 }  // namespace
 
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
-template <int kD, bool kBf16, int kPolyEvery>
+// kDyn: work items are claimed from a global atomic counter by the producer warp and broadcast to the other roles
+//       through a 2-deep smem ring (EXPERIMENTAL); otherwise the static snake schedule is used.
+template <int kD, bool kBf16, int kPolyEvery, bool kDyn>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
@@ -172,8 +174,41 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     B.kv_empty = a; a += 8 * C::STAGES;
   }
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::OFF_BAR + 480);
+  const uint32_t sc_full = bar0 + 400, sc_empty = bar0 + 416;              // dynamic scheduler ring (2 slots)
+  volatile int* sched_idx = reinterpret_cast<volatile int*>(smem_gen + C::OFF_BAR + 432);
+  // role-specific "next work item" (round = items fetched so far by this role)
+  auto producer_next = [&](int round) -> int {
+    if constexpr (kDyn) {
+      const uint32_t slot = round & 1, par = (round >> 1) & 1;
+      mbar_wait(sc_empty + 8 * slot, par ^ 1);
+      const int w = static_cast<int>(atomicAdd(p.sched_counter, 1u) - p.sched_base);
+      sched_idx[slot] = w;
+      mbar_arrive(sc_full + 8 * slot);
+      return w;
+    } else {
+      return sched_work(round, p.comm.n_comm);
+    }
+  };
+  auto consumer_next = [&](int round) -> int {
+    if constexpr (kDyn) {
+      const uint32_t slot = round & 1, par = (round >> 1) & 1;
+      mbar_wait(sc_full + 8 * slot, par);
+      const int w = sched_idx[slot];
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(sc_empty + 8 * slot);
+      return w;
+    } else {
+      return sched_work(round, p.comm.n_comm);
+    }
+  };
 
   if (threadIdx.x == 0) {
+    if constexpr (kDyn) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(sc_full + 8 * s, 1);
+        mbar_init(sc_empty + 8 * s, 9);    // MMA warp + 8 softmax warps
+      }
+    }
     for (int t = 0; t < 2; ++t) {
       mbar_init(B.q_full[t], 1);
       mbar_init(B.q_empty[t], 1);
@@ -210,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       int q_flag_ok = -1, k_flag_ok = -1;
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+        if (!decode_work(p, producer_next(round), wk)) break;
         const int qf = p.qseg[wk.qseg].flag;
         if (qf >= 0 && qf != q_flag_ok) { wait_flag(p, qf); q_flag_ok = qf; }
         for (int t = 0; t < wk.ntile; ++t) {
@@ -271,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       };
       for (int round = 0;; ++round) {
         Work wk;
-        if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+        if (!decode_work(p, consumer_next(round), wk)) break;
         const int nt = wk.ntile;
         TileIter it;
         it.init(p, wk);
@@ -338,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
-      if (!decode_work(p, sched_work(round, p.comm.n_comm), wk)) break;
+      if (!decode_work(p, consumer_next(round), wk)) break;
       if (t >= wk.ntile) continue;
       const int qpos = wk.pos0 + (t * BM + row) * p.q_pos_stride;
       const int qlo_t = wk.pos0 + t * BM * p.q_pos_stride;
@@ -535,10 +570,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly>
+template <int kD, bool kBf16, int kPoly, bool kDyn>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -555,11 +590,13 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  if (p.dyn_sched)
+    return p.poly_every == 0 ? launch_impl<kD, kBf16, 0, true>(p, num_sms, stream) : launch_impl<kD, kBf16, 6, true>(p, num_sms, stream);
   switch (p.poly_every) {
-    case 0: return launch_impl<kD, kBf16, 0>(p, num_sms, stream);
-    case 3: return launch_impl<kD, kBf16, 3>(p, num_sms, stream);
-    case 6: return launch_impl<kD, kBf16, 6>(p, num_sms, stream);
-    default: return launch_impl<kD, kBf16, 4>(p, num_sms, stream);
+    case 0: return launch_impl<kD, kBf16, 0, false>(p, num_sms, stream);
+    case 3: return launch_impl<kD, kBf16, 3, false>(p, num_sms, stream);
+    case 4: return launch_impl<kD, kBf16, 4, false>(p, num_sms, stream);
+    default: return launch_impl<kD, kBf16, 6, false>(p, num_sms, stream);
   }
 }
 

@@ -104,6 +104,10 @@ struct FwdParams {
   const float* k_scale;               // (B, Hkv, ceil(Sk/128))
   const float* v_scale;               // (B, Hkv)
   int64_t q_scale_sb, q_scale_sh, k_scale_sb, k_scale_sh;
+  // dynamic tile scheduler (kDyn instantiations only; EXPERIMENTAL, LCA_B200_DYN_SCHED=1)
+  uint32_t* sched_counter;            // monotonic device counter shared by the compute CTAs of a launch
+  uint32_t sched_base;                // counter value at launch start (host-tracked: += total_work + compute CTAs)
+  int dyn_sched;
 };
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -148,6 +152,9 @@ struct BwdParams {
   const uint32_t* flags;              // arrival flags (fused path)
   uint32_t flag_epoch;
   CommParams comm;
+  uint32_t* sched_counter;            // dynamic tile scheduler (see FwdParams)
+  uint32_t sched_base;
+  int dyn_sched;
 };
 
 }  // namespace lca
