@@ -16,7 +16,6 @@ from __future__ import annotations
 import importlib.util
 from typing import Optional
 
-import torch
 import torch.distributed as dist
 
 from .parallel.mesh import MeshSpec, build_mesh_spec

@@ -11,7 +11,6 @@ over the sequence-parallel group by :func:`allreduce_sp_grads` (the reference le
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Optional
 

@@ -20,7 +20,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from ..parallel.layout import PosSpec, Seg, group_tensor, has_groups, pos_min_max, pos_tensor
+from ..parallel.layout import PosSpec, group_tensor, has_groups, pos_min_max, pos_tensor
 from . import native, ref_attention
 
 

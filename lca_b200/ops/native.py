@@ -8,11 +8,11 @@ from __future__ import annotations
 
 import importlib
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 
-from ..parallel.layout import PosSpec, Seg
+from ..parallel.layout import PosSpec
 
 _C = None
 _LOAD_ERROR: Optional[str] = None

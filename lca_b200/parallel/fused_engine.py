@@ -32,14 +32,14 @@ from __future__ import annotations
 
 import os
 import socket
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
 
 from ..ops import native
 from ..ops.attention import AttnParams
-from .layout import Seg, canonical_variant, ring_positions, slice_pos
+from .layout import Seg, canonical_variant, ring_positions
 
 SIG_BYTES = 4096
 SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE, SIG_DKV, SIG_QA = 0, 16, 32, 48, 49, 64
@@ -404,7 +404,6 @@ class _FusedAttnFunc(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         """Collective backward (NCCL a2a + ring P2P around the tcgen05 backward kernels)."""
-        from ..globals import PROCESS_GROUP
         from .all_to_all import all_to_all_4D
         from .ring_attention import ring_attn_backward
         q, k, v, out, lse, lse_own = ctx.saved_tensors

@@ -13,7 +13,6 @@ from typing import Any, Optional
 import torch
 from torch import Tensor
 
-from ..globals import PROCESS_GROUP, group_size
 from ..kernels import AttnType, select_flash_attn_impl
 from ..parallel.all_to_all import SeqAllToAll4D
 from ..hybrid.attn_layer import _resolve_backend, _slice_alibi
