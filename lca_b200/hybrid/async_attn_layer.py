@@ -52,7 +52,7 @@ class AsyncLongContextAttention(torch.nn.Module):
         eng = None
         if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
             eng = self._fused_engine(query)
-        if eng is not None:
+        if eng is not None and eng.supports_shapes(query, key):
             return eng.attention(query, key, value, self.variant, softmax_scale, causal, window_size, softcap,
                                  alibi_slopes, deterministic)
 

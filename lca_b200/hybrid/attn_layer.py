@@ -102,7 +102,7 @@ class LongContextAttention(torch.nn.Module):
         eng = None
         if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
             eng = self._fused_engine(query)
-        if eng is not None:
+        if eng is not None and eng.supports_shapes(query, key):
             return eng.attention(query, key, value, self.variant, softmax_scale, causal, window_size, softcap,
                                  alibi_slopes, deterministic)
 
@@ -152,7 +152,7 @@ class LongContextAttentionQKVPacked(torch.nn.Module):
         eng = None
         if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
             eng = self._fused_engine(qkv)
-        if eng is not None:
+        if eng is not None and eng.supports_shapes(qkv[:, :, 0], qkv[:, :, 1]):
             # strided views of the packed tensor feed the push kernel directly: no unpack copy
             return eng.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.variant, softmax_scale, causal,
                                  window_size, softcap, alibi_slopes, deterministic)

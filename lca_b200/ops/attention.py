@@ -79,9 +79,21 @@ def pick_engine(q: torch.Tensor, engine: Optional[str]) -> str:
     if q.is_cuda:
         if native.supports(q):
             return "native"
-        if native.must_be_native():
+        if native.must_be_native() and not native.extension_loaded():
+            # a Blackwell box without the extension is a build problem, not something to paper over
             raise RuntimeError(f"native sm_100a kernels required but unusable: {native.why_not(q)}")
+        _warn_once(f"lca_b200: using the PyTorch attention engine on CUDA ({native.why_not(q)})")
     return "torch"
+
+
+_WARNED = set()
+
+
+def _warn_once(msg: str) -> None:
+    if msg not in _WARNED:
+        _WARNED.add(msg)
+        import warnings
+        warnings.warn(msg, stacklevel=3)
 
 
 def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,

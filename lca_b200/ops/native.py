@@ -86,6 +86,10 @@ def available() -> bool:
     return _load() is not None and _is_blackwell(torch.cuda.current_device())
 
 
+def extension_loaded() -> bool:
+    return _load() is not None
+
+
 def must_be_native() -> bool:
     """On a Blackwell box the native path is mandatory unless explicitly waived."""
     if os.environ.get("LCA_B200_ALLOW_FALLBACK", "0") == "1":

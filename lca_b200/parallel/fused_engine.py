@@ -95,6 +95,12 @@ class FusedUSPEngine:
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
         self.sig = _Slab(SIG_BYTES, sp_group, device)
 
+    def supports_shapes(self, q, k) -> bool:
+        """Shapes the push CTAs / kernels can handle; anything else takes the collective path."""
+        rows, H, Hkv = q.shape[1], q.shape[2], k.shape[2]
+        return (rows % 8 == 0 and k.shape[1] == rows and H % self.U == 0
+                and (Hkv % self.U == 0 or self.U % Hkv == 0) and H % Hkv == 0)
+
     # ------------------------------------------------------------------------------ workspace
     def _ensure(self, B, rows, H, Hkv, D, esz):
         U, R = self.U, self.R
