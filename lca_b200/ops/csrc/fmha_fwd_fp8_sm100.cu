@@ -480,17 +480,23 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
         if (lane == 0) mbar_arrive(B.p_full[t]);
         ++j;
       }
-      // ---- epilogue: O / l -> 16-bit -> smem (XOR-swizzled 16B chunks) -> coalesced global stores
-      uint8_t* stage = smem_gen + C::OFF_Q + t * C::TILE_BYTES;
+      // ---- epilogue: O * (sv / l) -> bf16, stored straight from registers (each thread owns one 256-byte output row).
+      // NOTE: unlike the 16-bit kernel there is no smem staging here: the Q tile buffers are only 16 KB each, a
+      // 32 KB bf16 O tile would not fit in them.
       if (j > 0) {
         mbar_wait(B.o_full[t], oc & 1);
         ++oc;
         tc_fence_after();
       } else {
-        mbar_wait(B.q_full[t], qc & 1);   // Q landed (never consumed): safe to reuse its smem
+        mbar_wait(B.q_full[t], qc & 1);   // keep the Q barrier phases in step even when nothing was consumed
       }
       ++qc;
       const float inv = (l > 0.f) ? sv / l : 0.f;        // V's per-head scale folds into the normalisation
+      const int rows_t = min(BM, wk.nrows - t * BM);
+      const QSegD qs = p.qseg[wk.qseg];
+      uint8_t* orow = reinterpret_cast<uint8_t*>(qs.o_base) +
+                      2 * (wk.b * p.o_sb + static_cast<int64_t>(wk.h + p.o_head_off) * p.o_sh +
+                           (static_cast<int64_t>(qs.o_row0) + wk.seg_row0 + t * BM + row) * p.o_ss);
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
         uint32_t o[32];
@@ -501,48 +507,24 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0u;
         }
+        if (row < rows_t) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {   // 4 chunks of 8 elements (16 bytes)
-          uint4 w;
-          w.x = pack2<kBf16>(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-          w.y = pack2<kBf16>(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-          w.z = pack2<kBf16>(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-          w.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-          const int chunk = c * 4 + g;
-          *reinterpret_cast<uint4*>(stage + row * (kD * 2) + ((chunk ^ (row & 7)) << 4)) = w;
+          for (int g = 0; g < 4; ++g) {   // 4 chunks of 8 elements (16 bytes)
+            uint4 w;
+            w.x = pack2<kBf16>(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            w.y = pack2<kBf16>(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            w.z = pack2<kBf16>(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            w.w = pack2<kBf16>(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + (c * 4 + g) * 16) = w;
+          }
         }
       }
       tc_fence_before();
-      const int rows_t = min(BM, wk.nrows - t * BM);
       if (row < rows_t) {
         const float lse = (l > 0.f) ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
         p.lse[wk.b * p.lse_sb + wk.h * p.lse_sh + wk.row0 + t * BM + row] = lse;
-        float* lown = p.qseg[wk.qseg].lse_base;     // the token owner keeps the LSE too (used by the fused backward)
-        if (lown != nullptr)
-          lown[wk.b * p.lse_own_sb + static_cast<int64_t>(wk.h + p.o_head_off) * p.lse_own_sh + p.qseg[wk.qseg].o_row0 +
-               wk.seg_row0 + t * BM + row] = lse;
       }
-      named_bar_sync(1 + t, 128);
-      {
-        constexpr int LPR = kD / 8;          // lanes per row (16-byte chunks per row)
-        constexpr int RPI = 32 / LPR;        // rows per warp instruction
-        const QSegD qs = p.qseg[wk.qseg];
-        uint8_t* obase = reinterpret_cast<uint8_t*>(qs.o_base) +
-                         2 * (wk.b * p.o_sb + static_cast<int64_t>(wk.h + p.o_head_off) * p.o_sh);
-        const int64_t orow0 = static_cast<int64_t>(qs.o_row0) + wk.seg_row0 + t * BM;
-        const int chunk = lane % LPR;
-#pragma unroll 4
-        for (int i = 0; i < BM / (4 * RPI); ++i) {
-          const int r = i * 4 * RPI + (warp & 3) * RPI + lane / LPR;
-          if (r < rows_t) {
-            const uint4 w = *reinterpret_cast<const uint4*>(stage + r * (kD * 2) + ((chunk ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(obase + 2 * (orow0 + r) * p.o_ss + chunk * 16) = w;
-          }
-        }
-        if (qs.o_sig != nullptr) __threadfence_system();
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + t, 128);
+      named_bar_sync(1 + t, 128);            // every thread has finished reading O from TMEM
       if ((warp & 3) == 0 && lane == 0) {
         mbar_arrive(B.q_empty[t]);
         uint32_t* sig = p.qseg[wk.qseg].o_sig;
