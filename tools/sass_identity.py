@@ -1,0 +1,51 @@
+"""Compare the SASS instruction streams of kernel instantiations between two object files (or against a saved
+normalised dump).  Used after adding template-gated experimental code paths to prove that the default
+instantiations still compile to exactly the instructions that were validated on hardware.
+
+  python tools/sass_identity.py dump lca_b200/ops/build/fmha_fwd_sm100.o > /tmp/base.sass      # at the validated commit
+  python tools/sass_identity.py check /tmp/base.sass lca_b200/ops/build/fmha_fwd_sm100.o 'ELb0EEEv'   # later
+"""
+import re
+import subprocess
+import sys
+
+
+def dump(obj):
+    out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        if "Function :" in line:
+            cur = line.split(":", 1)[1].strip()
+            funcs[cur] = []
+        elif cur and re.match(r"^\s+/\*[0-9a-f]{4}\*/", line):
+            funcs[cur].append(re.sub(r"/\*[0-9a-f]{4,}\*/|/\* 0x[0-9a-f]+ \*/", "", line).strip())
+    return funcs
+
+
+def load(path):
+    funcs, cur = {}, None
+    for line in open(path):
+        if line.startswith("Function : "):
+            cur = line[len("Function : "):].strip()
+            funcs[cur] = []
+        elif cur:
+            funcs[cur].append(line.rstrip("\n"))
+    return funcs
+
+
+def key(name):
+    """Strip template arguments appended after validation (trailing `ELb0` flags) for matching."""
+    return re.sub(r"(ELb0)+EEEv", "EEEv", name)
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "dump":
+        for n, body in dump(sys.argv[2]).items():
+            print("Function : " + n)
+            print("\n".join(body))
+    else:
+        base, new = load(sys.argv[2]), dump(sys.argv[3])
+        newk = {key(n): b for n, b in new.items() if not re.search(r"ELb1EEEv", n) or key(n) == n}
+        bad = [n for n, b in base.items() if newk.get(key(n)) != b]
+        print(f"{len(base) - len(bad)}/{len(base)} instantiations identical")
+        sys.exit(1 if bad else 0)
