@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--ring-impl", default="zigzag", choices=["basic", "zigzag", "strip"])
     ap.add_argument("--no-causal", action="store_true")
     ap.add_argument("--backend", default=None, help="ours: auto|fused|collective")
+    ap.add_argument("--window", type=int, default=-1, help="sliding window (left) in tokens; -1 = none (BASELINE config 4)")
+    ap.add_argument("--qkvpacked", action="store_true", help="LongContextAttentionQKVPacked (BASELINE config 5; MHA only)")
     return ap.parse_args()
 
 
@@ -129,7 +131,11 @@ def main():
                 print(json.dumps({"impl": "reference", "unavailable": f"import yunchang failed: {type(e).__name__}: {str(e)[:120]}"}))
             return
         set_seq_parallel_pg(U, R, rank, world)
-        attn = LongContextAttention(ring_impl_type=a.ring_impl, attn_type=AttnType.FA)
+        if a.qkvpacked:
+            from yunchang import LongContextAttentionQKVPacked
+            attn = LongContextAttentionQKVPacked(ring_impl_type=a.ring_impl, attn_type=AttnType.FA)
+        else:
+            attn = LongContextAttention(ring_impl_type=a.ring_impl, attn_type=AttnType.FA)
         launches = lambda: 0
         native_ok = None
     else:
@@ -138,7 +144,11 @@ def main():
         from lca_b200.ops import native
 
         set_seq_parallel_pg(U, R, rank, world)
-        attn = LongContextAttention(ring_impl_type=a.ring_impl, backend=a.backend)
+        if a.qkvpacked:
+            from lca_b200 import LongContextAttentionQKVPacked
+            attn = LongContextAttentionQKVPacked(ring_impl_type=a.ring_impl, backend=a.backend)
+        else:
+            attn = LongContextAttention(ring_impl_type=a.ring_impl, backend=a.backend)
         launches = lambda: native.LAUNCHES
         native_ok = native.available()
         assert native_ok, "native sm_100a extension not available on this GPU box"
@@ -158,13 +168,22 @@ def main():
     dout = host_do.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    kw = dict(causal=causal)
+    if a.window >= 0:
+        kw["window_size"] = (a.window, 0 if causal else a.window)
+
+    def call(q, k, v):
+        if a.qkvpacked:
+            return attn(torch.stack([q, k, v], dim=2), **kw)      # (B, S/P, 3, H, D)
+        return attn(q, k, v, **kw)
+
     def step(q, k, v):
         if need_grad:
-            out = attn(q, k, v, causal=causal)
+            out = call(q, k, v)
             out.backward(dout)
             return out
         with torch.no_grad():
-            return attn(q, k, v, causal=causal)
+            return call(q, k, v)
 
     def barrier():
         if need_dist and world > 1:
@@ -244,7 +263,7 @@ def main():
             "impl": a.impl,
             "config": {"model": "LongContextAttention(ring_impl_type=%s)" % a.ring_impl, "global_batch": B,
                        "seq_len": S, "heads": H, "kv_heads": Hkv, "head_dim": D, "causal": causal,
-                       "parallelism": f"ulysses{U}xring{R}", "mode": a.mode,
+                       "parallelism": f"ulysses{U}xring{R}", "mode": a.mode, "window": a.window, "qkvpacked": a.qkvpacked,
                        "l2": "256 MiB flush write between timed iterations; per-rank q+k+v+o also exceed L2",
                        "native_kernels": native_ok},
             "clocks": clocks,
