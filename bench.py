@@ -160,9 +160,11 @@ def main():
     need_grad = a.mode == "fwdbwd"
 
     def to_dev(non_blocking=True):
+        """This step's inputs: q, k, v (and the upstream gradient dO in fwd+bwd mode) from pinned host memory."""
         ts = [t.to(dev, non_blocking=non_blocking) for t in host]
         if need_grad:
             ts = [t.requires_grad_() for t in ts]
+            ts.append(host_do.to(dev, non_blocking=non_blocking))
         return ts
 
     dout = host_do.to(dev)
@@ -177,10 +179,10 @@ def main():
             return attn(torch.stack([q, k, v], dim=2), **kw)      # (B, S/P, 3, H, D)
         return attn(q, k, v, **kw)
 
-    def step(q, k, v):
+    def step(q, k, v, do=None):
         if need_grad:
             out = call(q, k, v)
-            out.backward(dout)
+            out.backward(dout if do is None else do)
             return out
         with torch.no_grad():
             return call(q, k, v)
@@ -191,7 +193,7 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident timing
-    q, k, v = to_dev(False)
+    q, k, v = to_dev(False)[:3]
     for _ in range(max(a.warmup, 3)):
         step(q, k, v)
         flush.fill_(1)
@@ -253,7 +255,7 @@ def main():
         flops *= 3.5
     tflops = flops / (ms * 1e-3) / 1e12
     tflops_e2e = flops / (ms_e2e * 1e-3) / 1e12
-    h2d = sum(t.numel() * t.element_size() for t in host)
+    h2d = sum(t.numel() * t.element_size() for t in host) + (host_do.numel() * host_do.element_size() if need_grad else 0)
     if rank == 0:
         print(json.dumps({
             "metric": "attention_tflops_" + ("fwd_bwd" if need_grad else "fwd"),
