@@ -78,6 +78,61 @@ class _Slab:
         C.symm_free(self.ptr)
 
 
+class _VmmSlab:
+    """Opt-in slab provider (``LCA_B200_SLAB=vmm``): ``torch.distributed._symmetric_memory``.
+
+    The default ``_Slab`` shares a ``cudaMalloc`` allocation through legacy CUDA IPC, which turns on device-wide
+    peer access: from then on every *later* ``cudaMalloc`` of a rank has to be mapped into its peers' contexts,
+    and that mapping can wait for a peer's running kernel.  A persistent kernel that spins on a flag of a rank
+    whose host is inside ``cudaMalloc`` would then never be released (suspected cause of the one hang seen in
+    round 1: fused forward + NCCL backward at N=4, where NCCL's lazy communicator creation de-synchronises
+    the hosts while the caching allocator is still growing).  The torch provider allocates with the CUDA VMM API
+    (``cuMemCreate`` / ``cuMemMap`` / ``cuMemSetAccess``): only the slab itself is peer-visible, ordinary
+    allocations never touch a peer.  It also exposes the NVLS multicast address (``multicast_ptr``) that the
+    round-2 K/V broadcast wants.  Same interface as ``_Slab``.  Not yet exercised on hardware.
+    """
+
+    def __init__(self, nbytes: int, group, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        self.nbytes = nbytes
+        self.device = device
+        pg = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.hdl = symm.rendezvous(self.buf, pg)          # collective: also orders the zero-fill before any push
+        self.ptr = int(self.buf.data_ptr())
+        self.peer_ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        me = dist.get_rank(pg)
+        if self.peer_ptrs[me] != self.ptr:
+            raise RuntimeError("symmetric memory handle does not describe the local buffer")
+        try:
+            self.multicast_ptr = int(self.hdl.multicast_ptr or 0)
+        except Exception:   # noqa: BLE001 - no NVLS on this box / build
+            self.multicast_ptr = 0
+        dist.barrier(group=pg)
+
+    def tensor(self, offset: int, shape, dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        return self.buf[offset:offset + nb].view(dtype).view(*shape)
+
+    def close(self):
+        self.hdl = None
+        self.buf = None
+
+
+def _make_slab(nbytes: int, group, device: torch.device):
+    kind = os.environ.get("LCA_B200_SLAB", "ipc")
+    if kind == "vmm":
+        return _VmmSlab(nbytes, group, device)
+    if kind != "ipc":
+        raise ValueError(f"LCA_B200_SLAB={kind!r}: expected 'ipc' or 'vmm'")
+    return _Slab(nbytes, group, device)
+
+
 class FusedUSPEngine:
     def __init__(self, sp_group, U: int, R: int, u: int, r: int, device: torch.device):
         self.group, self.U, self.R, self.u, self.r = sp_group, U, R, u, r
@@ -93,7 +148,7 @@ class FusedUSPEngine:
         self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "8"))
         self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
-        self.sig = _Slab(SIG_BYTES, sp_group, device)
+        self.sig = _make_slab(SIG_BYTES, sp_group, device)
 
     def supports_shapes(self, q, k) -> bool:
         """Shapes the push CTAs / kernels can handle; anything else takes the collective path."""
@@ -130,7 +185,7 @@ class FusedUSPEngine:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(group=self.group)      # nobody may still be writing into the old slab
                 self.slab.close()
-            self.slab = _Slab(total, self.group, self.device)
+            self.slab = _make_slab(total, self.group, self.device)
         self.key = key
 
     # ------------------------------------------------------------------------------ forward
