@@ -109,6 +109,11 @@ struct SchedState {
   at::Tensor counter;
   uint32_t base = 0;
 };
+// packed fp32x2 element-wise arithmetic in the softmax / dS stages (EXPERIMENTAL, LCA_B200_F32X2=1)
+static int f32x2_enabled() {
+  static int e = [] { const char* v = std::getenv("LCA_B200_F32X2"); return (v && std::atoi(v) == 1) ? 1 : 0; }();
+  return e;
+}
 static bool dyn_sched_enabled() {
   static bool e = [] { const char* v = std::getenv("LCA_B200_DYN_SCHED"); return v && std::atoi(v) == 1; }();
   return e;
@@ -222,6 +227,7 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   {
     static int poly = [] { const char* e = std::getenv("LCA_B200_POLY_EVERY"); return e ? std::atoi(e) : 6; }();
     p.poly_every = poly;
+    p.f32x2 = f32x2_enabled();
   }
   p.lse_own_sb = out.size(2) * out.size(1);      // owners keep (B, H_total, rows) next to their (B, rows, H_total, D) output
   p.lse_own_sh = out.size(1);
@@ -429,6 +435,7 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
               lse2.sizes() == delta.sizes() && lse2.stride(2) == 1 && delta.strides() == lse2.strides(), "lse2/delta");
   TORCH_CHECK(lse2.size(0) == B && lse2.size(1) == Hq, "lse2 shape");
   std::memset(&p, 0, sizeof(p));
+  p.f32x2 = f32x2_enabled();
   make_tmap(&p.tm_x0, x0, "x0", 128);
   make_tmap(&p.tm_x1, x1, "x1", 128);
   make_tmap(&p.tm_y0, y0, "y0", 64);

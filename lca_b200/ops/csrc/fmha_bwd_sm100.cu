@@ -176,7 +176,7 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 }  // namespace
 
 // kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
@@ -313,8 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             for (int i = 0; i < 2; ++i) {
               const int c = lane + 32 * i;
               const bool ok = c < it.nvalid;
-              stat[st * 2 * BY + c] = ok ? l2[it.y_row0 + c] : INFINITY;
-              stat[st * 2 * BY + BY + c] = ok ? dl[it.y_row0 + c] : 0.f;
+              if constexpr (kPk) {       // packed variant: statistics are staged negated (no negate modifiers on FFMA2/FADD2)
+                stat[st * 2 * BY + c] = ok ? -l2[it.y_row0 + c] : -INFINITY;
+                stat[st * 2 * BY + BY + c] = ok ? -dl[it.y_row0 + c] : 0.f;
+              } else {
+                stat[st * 2 * BY + c] = ok ? l2[it.y_row0 + c] : INFINITY;
+                stat[st * 2 * BY + BY + c] = ok ? dl[it.y_row0 + c] : 0.f;
+              }
             }
             mbar_arrive(st_full + 8 * st);
           }
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = half * 32 + i;
-              const float dl = kIsDKV ? st_dl[col] : delta_r;
+              const float dl = kIsDKV ? (kPk ? -st_dl[col] : st_dl[col]) : delta_r;
               float x = __uint_as_float(t0[i]) * p.scale;
               float extra = 1.f;
               if (p.softcap > 0.f) {
@@ -511,13 +516,32 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
               dlv[0] = b4.x; dlv[1] = b4.y; dlv[2] = b4.z; dlv[3] = b4.w;
             } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { l2v[e] = lse2_r; dlv[e] = delta_r; }
+              for (int e = 0; e < 4; ++e) { l2v[e] = kPk ? -lse2_r : lse2_r; dlv[e] = kPk ? -delta_r : delta_r; }
             }
             float pv[4], dv[4];
+            if constexpr (kPk) {
+              // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair (experimental, LCA_B200_F32X2=1)
+              // l2v / dlv hold the NEGATED statistics in this variant: x = T0*mul + (-lse2), d = T1 + (-delta)
+              const uint64_t mul2 = ptx::pack_f32x2(mul, mul);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              pv[e] = ex2(fmaf(__uint_as_float(t0[c + e]), mul, -l2v[e]));
-              dv[e] = pv[e] * (__uint_as_float(t1[c + e]) - dlv[e]);
+              for (int e = 0; e < 4; e += 2) {
+                float x0, x1;
+                ptx::unpack_f32x2(ptx::fma_f32x2(
+                    ptx::pack_f32x2(__uint_as_float(t0[c + e]), __uint_as_float(t0[c + e + 1])), mul2,
+                    ptx::pack_f32x2(l2v[e], l2v[e + 1])), x0, x1);
+                pv[e] = ex2(x0);
+                pv[e + 1] = ex2(x1);
+                const uint64_t d = ptx::add_f32x2(
+                    ptx::pack_f32x2(__uint_as_float(t1[c + e]), __uint_as_float(t1[c + e + 1])),
+                    ptx::pack_f32x2(dlv[e], dlv[e + 1]));
+                ptx::unpack_f32x2(ptx::mul_f32x2(ptx::pack_f32x2(pv[e], pv[e + 1]), d), dv[e], dv[e + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                pv[e] = ex2(fmaf(__uint_as_float(t0[c + e]), mul, -l2v[e]));
+                dv[e] = pv[e] * (__uint_as_float(t1[c + e]) - dlv[e]);
+              }
             }
             if constexpr (kIsDKV) {
               pp[(c >> 1)] = pack2<kBf16>(pv[0], pv[1]);
@@ -598,10 +622,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -618,6 +642,9 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
+  if (p.f32x2 && !p.dyn_sched)        // experimental packed element-wise stage (static schedule only)
+    return is_dkv ? launch_impl<kD, kBf16, true, false, true>(p, num_sms, stream)
+                  : launch_impl<kD, kBf16, false, false, true>(p, num_sms, stream);
   if (p.dyn_sched)
     return is_dkv ? launch_impl<kD, kBf16, true, true>(p, num_sms, stream) : launch_impl<kD, kBf16, false, true>(p, num_sms, stream);
   return is_dkv ? launch_impl<kD, kBf16, true, false>(p, num_sms, stream) : launch_impl<kD, kBf16, false, false>(p, num_sms, stream);

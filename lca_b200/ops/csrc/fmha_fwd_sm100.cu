@@ -146,8 +146,10 @@ struct Bars {
 
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
 // kDyn: work items are claimed from a global atomic counter by the producer warp and broadcast to the other roles
+// kPk: the unmasked softmax runs on packed fp32x2 instructions (FFMA2 / FADD2): scale-and-subtract, the polynomial
+//      exp2 and the row sum issue once per element pair (experimental, opt-in: LCA_B200_F32X2=1)
 //       through a 2-deep smem ring (EXPERIMENTAL); otherwise the static snake schedule is used.
-template <int kD, bool kBf16, int kPolyEvery, bool kDyn>
+template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
@@ -454,13 +456,54 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         // ---- P = exp2(x*mul - m), row sum, pack, store over S
         float rs = 0.f;
         if (general) {
+          if constexpr (kPk) {
+            const uint64_t mul2 = ptx::pack_f32x2(mul, mul), nsub2 = ptx::pack_f32x2(-sub, -sub);
+            uint64_t acc_a = ptx::pack_f32x2(0.f, 0.f), acc_b = acc_a;
+#pragma unroll
+            for (int c = 0; c < 128; c += 2) {
+              float x0, x1;
+              ptx::unpack_f32x2(
+                  ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), mul2, nsub2), x0, x1);
+              const float p0 = ex2(x0), p1 = ex2(x1);      // masked entries are -inf -> exactly 0
+              if (c & 2) acc_b = ptx::add_f32x2(acc_b, ptx::pack_f32x2(p0, p1));
+              else acc_a = ptx::add_f32x2(acc_a, ptx::pack_f32x2(p0, p1));
+              v[c >> 1] = pack2<kBf16>(p0, p1);
+            }
+            float s0, s1;
+            ptx::unpack_f32x2(ptx::add_f32x2(acc_a, acc_b), s0, s1);
+            rs = s0 + s1;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 128; c += 2) {
+              const float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
+              const float p1 = ex2(fmaf(__uint_as_float(v[c + 1]), mul, -sub));
+              rs += p0 + p1;
+              v[c >> 1] = pack2<kBf16>(p0, p1);
+            }
+          }
+        } else if constexpr (kPk) {
+          const uint64_t mul2 = ptx::pack_f32x2(mul, mul), nsub2 = ptx::pack_f32x2(-sub, -sub);
+          uint64_t acc_a = ptx::pack_f32x2(0.f, 0.f), acc_b = acc_a;     // two chains: the adds of a row are serial
 #pragma unroll
           for (int c = 0; c < 128; c += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
-            const float p1 = ex2(fmaf(__uint_as_float(v[c + 1]), mul, -sub));
-            rs += p0 + p1;
+            const uint64_t x =
+                ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), mul2, nsub2);
+            float p0, p1;
+            if (kPolyEvery > 0 && ((c >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0) {
+              ptx::ex2_poly_x2(x, p0, p1);
+            } else {
+              float x0, x1;
+              ptx::unpack_f32x2(x, x0, x1);
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            if (c & 2) acc_b = ptx::add_f32x2(acc_b, ptx::pack_f32x2(p0, p1));
+            else acc_a = ptx::add_f32x2(acc_a, ptx::pack_f32x2(p0, p1));
             v[c >> 1] = pack2<kBf16>(p0, p1);
           }
+          float s0, s1;
+          ptx::unpack_f32x2(ptx::add_f32x2(acc_a, acc_b), s0, s1);
+          rs = s0 + s1;
         } else {
           // unmasked tiles (the bulk of the work): every kPolyEvery-th pair takes the FMA-pipe exp2
 #pragma unroll
@@ -570,10 +613,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly, bool kDyn>
+template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -590,6 +633,14 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
+    switch (p.poly_every) {
+      case 0: return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);
+      case 3: return launch_impl<kD, kBf16, 3, false, true>(p, num_sms, stream);
+      case 4: return launch_impl<kD, kBf16, 4, false, true>(p, num_sms, stream);
+      default: return launch_impl<kD, kBf16, 6, false, true>(p, num_sms, stream);
+    }
+  }
   if (p.dyn_sched)
     return p.poly_every == 0 ? launch_impl<kD, kBf16, 0, true>(p, num_sms, stream) : launch_impl<kD, kBf16, 6, true>(p, num_sms, stream);
   switch (p.poly_every) {

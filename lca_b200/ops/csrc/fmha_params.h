@@ -108,6 +108,7 @@ struct FwdParams {
   uint32_t* sched_counter;            // monotonic device counter shared by the compute CTAs of a launch
   uint32_t sched_base;                // counter value at launch start (host-tracked: += total_work + compute CTAs)
   int dyn_sched;
+  int f32x2;                          // packed fp32x2 softmax arithmetic (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
 };
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -155,6 +156,7 @@ struct BwdParams {
   uint32_t* sched_counter;            // dynamic tile scheduler (see FwdParams)
   uint32_t sched_base;
   int dyn_sched;
+  int f32x2;                          // packed fp32x2 element-wise stage (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
 };
 
 }  // namespace lca

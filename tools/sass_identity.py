@@ -4,7 +4,11 @@ instantiations still compile to exactly the instructions that were validated on 
 
   python tools/sass_identity.py dump lca_b200/ops/build/fmha_fwd_sm100.o > /tmp/base.sass      # at the validated commit
   python tools/sass_identity.py check /tmp/base.sass lca_b200/ops/build/fmha_fwd_sm100.o 'ELb0EEEv'   # later
+  python tools/sass_identity.py hash lca_b200/ops/build/*.o > profiles/sass_hashes_r1.json             # compact baseline
+  python tools/sass_identity.py checkhash profiles/sass_hashes_r1.json lca_b200/ops/build/*.o
 """
+import hashlib
+import json
 import re
 import subprocess
 import sys
@@ -38,8 +42,25 @@ def key(name):
     return re.sub(r"(ELb0)+EEEv", "EEEv", name)
 
 
+def hashes(objs):
+    out = {}
+    for o in objs:
+        for n, body in dump(o).items():
+            out[key(n)] = hashlib.sha1("\n".join(body).encode()).hexdigest()
+    return out
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "dump":
+    if sys.argv[1] == "hash":
+        print(json.dumps(hashes(sys.argv[2:]), indent=0, sort_keys=True))
+    elif sys.argv[1] == "checkhash":
+        base, new = json.load(open(sys.argv[2])), hashes(sys.argv[3:])
+        bad = [n for n, h in base.items() if new.get(n) != h]
+        for n in bad:
+            print("DIFFERS:", n)
+        print(f"{len(base) - len(bad)}/{len(base)} validated instantiations identical; {len(set(new) - set(base))} new")
+        sys.exit(1 if bad else 0)
+    elif sys.argv[1] == "dump":
         for n, body in dump(sys.argv[2]).items():
             print("Function : " + n)
             print("\n".join(body))

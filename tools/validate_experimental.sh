@@ -1,0 +1,48 @@
+#!/usr/bin/env bash
+# First GPU call of a round: validate the opt-in (template-gated) kernel variants that were written without hardware
+# and measure them against the default build.  One GPU, ~6 minutes.  Everything lands in gpurun_out/experimental/.
+#
+#   gpurun --timeout 900 -- 'bash tools/validate_experimental.sh'
+#
+# Each step runs under its own timeout so a hung kernel cannot eat the box.  Exit code = number of failed steps.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/experimental
+mkdir -p "$OUT"
+fail=0
+step() {   # step <name> <timeout_s> <env...> -- <cmd...>
+  local name=$1 tmo=$2; shift 2
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done
+  shift
+  echo "=== $name (${envs[*]:-default})"
+  if env ${envs[@]+"${envs[@]}"} timeout "$tmo" "$@" > "$OUT/$name.log" 2>&1; then
+    echo "    ok"; tail -n 3 "$OUT/$name.log" | sed 's/^/    /'
+  else
+    echo "    FAILED (exit $?)"; tail -n 15 "$OUT/$name.log" | sed 's/^/    /'; fail=$((fail + 1))
+  fi
+}
+
+# 0. reference point: default build
+step perf_default 120 S=32768 -- python tools/gpu_time_passes.py
+
+# 1. packed fp32x2 softmax / dS arithmetic (FFMA2 / FADD2 / FMUL2)
+step tests_f32x2 420 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
+step perf_f32x2 120 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
+for pe in 3 4; do
+  step perf_f32x2_poly$pe 120 LCA_B200_F32X2=1 LCA_B200_POLY_EVERY=$pe S=32768 -- python tools/gpu_time_passes.py
+done
+
+# 2. dynamic tile scheduler
+step tests_dyn 420 LCA_B200_DYN_SCHED=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
+step perf_dyn 120 LCA_B200_DYN_SCHED=1 S=32768 -- python tools/gpu_time_passes.py
+
+# 3. fp8 forward (tcgen05 kind::f8f6f4)
+step tests_fp8 300 LCA_B200_EXPERIMENTAL_FP8=1 -- python -m pytest tests/test_fp8.py -x -q -m gpu
+
+grep -h '"name"' "$OUT"/perf_*.log 2>/dev/null | sed 's/^/  /' > "$OUT/summary.txt"
+for f in "$OUT"/perf_*.log; do echo "$(basename "$f" .log): $(grep -h '"name"' "$f" | python -c '
+import sys, json
+print("  ".join("%s %.3f ms" % (d["name"].split("(")[0], d["ms"]) for d in map(json.loads, sys.stdin)))')"; done | tee -a "$OUT/summary.txt"
+echo "failed steps: $fail"
+exit $fail
