@@ -73,28 +73,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     pyinc = f"-I{sysconfig.get_paths()['include']}"
     cxx11 = int(bool(torch._C._GLIBCXX_USE_CXX11_ABI))
 
-    objs, rebuilt = [], False
-    for src in cus:
+    # every translation unit is an independent job; nvcc/g++ run concurrently (a cold build is dominated by the two
+    # attention kernels' template instantiations)
+    jobs = []      # (cmd, stamp_file, stamp)
+    objs: List[str] = []
+    for src in cus + cpps:
         obj = BUILD / (src.stem + ".o")
         stamp_file = BUILD / (src.stem + ".stamp")
         stamp = _stamp([str(src)] + headers)
-        if force or not obj.exists() or not stamp_file.exists() or stamp_file.read_text() != stamp:
-            _run([nvcc, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
-                  "-Xptxas", "-v" if verbose else "-O3", f"-I{CSRC}", "-c", str(src), "-o", str(obj)], verbose)
-            stamp_file.write_text(stamp)
-            rebuilt = True
         objs.append(str(obj))
-    for src in cpps:
-        obj = BUILD / (src.stem + ".o")
-        stamp_file = BUILD / (src.stem + ".stamp")
-        stamp = _stamp([str(src)] + headers)
-        if force or not obj.exists() or not stamp_file.exists() or stamp_file.read_text() != stamp:
-            _run(["g++", "-O2", "-std=c++17", "-fPIC", "-Wno-deprecated-declarations", f"-D_GLIBCXX_USE_CXX11_ABI={cxx11}",
-                  f"-DTORCH_EXTENSION_NAME={EXT_NAME}", "-DTORCH_API_INCLUDE_EXTENSION_H", f"-I{CSRC}",
-                  f"-I{cuda}/include", *tinc, pyinc, "-c", str(src), "-o", str(obj)], verbose)
+        if not (force or not obj.exists() or not stamp_file.exists() or stamp_file.read_text() != stamp):
+            continue
+        if src.suffix == ".cu":
+            cmd = [nvcc, *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
+                   "-Xptxas", "-v" if verbose else "-O3", f"-I{CSRC}", "-c", str(src), "-o", str(obj)]
+        else:
+            cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-Wno-deprecated-declarations",
+                   f"-D_GLIBCXX_USE_CXX11_ABI={cxx11}", f"-DTORCH_EXTENSION_NAME={EXT_NAME}",
+                   "-DTORCH_API_INCLUDE_EXTENSION_H", f"-I{CSRC}", f"-I{cuda}/include", *tinc, pyinc, "-c", str(src),
+                   "-o", str(obj)]
+        jobs.append((cmd, stamp_file, stamp))
+    rebuilt = bool(jobs)
+    if jobs:
+        from concurrent.futures import ThreadPoolExecutor
+        workers = max(1, min(len(jobs), int(os.environ.get("LCA_B200_BUILD_JOBS", os.cpu_count() or 1))))
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            for fut in [pool.submit(_run, cmd, verbose) for cmd, _, _ in jobs]:
+                fut.result()                      # re-raises the first failing step
+        for _, stamp_file, stamp in jobs:
             stamp_file.write_text(stamp)
-            rebuilt = True
-        objs.append(str(obj))
 
     out = so_path()
     if rebuilt or force or not out.exists():
