@@ -283,6 +283,24 @@ class FusedUSPEngine:
                     segs.append([sr * Sr + row0, s.count, s.start, SIG_KV + sr * U + su, 0])
         return segs
 
+    def _bwd_segments(self, variant: str, rows: int):
+        """Every token shard of the mesh as a segment list over the (B, S, ...) all-rank staging layout of the
+        owner-computes backward -> (all_segs, mine, tiles_of_me); a segment is (src sp-rank, staging row0, nrows,
+        global position of its first token).  ``mine`` = segments of my ring block (the stationary rows of both
+        passes); ``tiles_of_me`` = 128-row tiles the whole mesh produces for tokens I own (completion count)."""
+        U, R, u, r = self.U, self.R, self.u, self.r
+        Sr = U * rows
+        all_segs = []
+        for sr in [(r - i) % R for i in range(R)]:        # own ring block first, then "ring step" order
+            pos = ring_positions(variant, sr, R, Sr)
+            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
+            for su in us:
+                for sg, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
+                    all_segs.append((sr * U + su, sr * Sr + row0, sg.count, sg.start))
+        mine = [t for t in all_segs if t[0] // U == r]
+        tiles_of_me = sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == self.me)
+        return all_segs, mine, tiles_of_me
+
     # ------------------------------------------------------------------------------ backward
     def backward(self, dout, q, k, v, out, lse, lse_own, variant: str, p: AttnParams):
         """Owner-computes backward (default whenever ``Hkv % U == 0``).
@@ -323,16 +341,7 @@ class FusedUSPEngine:
         stride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
         alibi = self._alibi(p, Hl)
-        # every token shard of the mesh as a segment list over the (B, S, ...) all-rank staging layout
-        all_segs = []                     # (src, row0, nrows, pos0)
-        for sr in [(r - i) % R for i in range(R)]:
-            pos = ring_positions(variant, sr, R, Sr)
-            us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
-            for su in us:
-                for sg, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
-                    all_segs.append((sr * U + su, sr * Sr + row0, sg.count, sg.start))
-        mine = [t for t in all_segs if t[0] // U == r]            # my ring block (queries I own after the Ulysses gather)
-        tiles_of_me = sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == self.me)
+        all_segs, mine, tiles_of_me = self._bwd_segments(variant, rows)
         ksegs = [[row0, n, pos0, SIG_KV + src, 0] for (src, row0, n, pos0) in all_segs]
         # ---- pass 1: dQ of my ring block's queries (stationary) against all K/V (streamed)
         xq = [[row0, n, pos0, 0, row0 - src * rows, SIG_QA + src, slab.peer_ptrs[src] + self.off_o, 0,

@@ -66,3 +66,75 @@ def test_segments_describe_each_ranks_problem(U, R, variant):
             torch.testing.assert_close(out, ref[:, tok], atol=1e-5, rtol=1e-5)
             torch.testing.assert_close(lse, ref_lse[:, :, tok], atol=1e-5, rtol=1e-5)
             assert n_my_tiles == sum((s[1] + 127) // 128 for s in qsegs if s[0] // rows == u)
+
+
+@pytest.mark.parametrize("U,R", [(1, 2), (2, 1), (2, 2), (4, 2), (2, 4), (1, 8), (8, 1), (1, 4)])
+@pytest.mark.parametrize("variant", ["basic", "zigzag", "stripe"])
+def test_owner_computes_backward_segments_cover_every_gradient_once(U, R, variant):
+    """Host logic of the owner-computes backward (``FusedUSPEngine.backward``): the stationary/streamed segment lists
+    of both passes and the owner scatter (``row0 - src*rows``) must produce every (token, head) of dQ, dK, dV exactly
+    once and equal to the global gradient.  The all-rank staging (q/dO/k/v of every sp-rank in sp-rank-major order,
+    head slice of this Ulysses rank) is emulated with torch."""
+    from lca_b200.ops.ref_attention import attn_block_bwd_ref
+    P, rows, H, D = U * R, 8, 2 * U, 8
+    S, Hl = P * rows, H // U
+    g = torch.Generator().manual_seed(1)
+    q, k, v, do = (torch.randn(1, S, H, D, generator=g) for _ in range(4))
+    win = (S // 2, 0)
+    pos_all = torch.arange(S)
+    p = AttnParams.make(q, None, True, win)
+    out, lse = attn_block_fwd_ref(q, k, v, pos_all, pos_all, p.softmax_scale, True, win)
+    rdq, rdk, rdv = attn_block_bwd_ref(do, q, k, v, out, lse, pos_all, pos_all, p.softmax_scale, True, win)
+    own = {(su, sr): local_token_index(variant, S, su, sr, U, R) for su in range(U) for sr in range(R)}
+    tok_of_stage = torch.cat([own[(src % U, src // U)] for src in range(P)])       # staging row -> global token id
+    stride = R if variant == "stripe" else 1
+    dq = torch.full((S, H, D), float("nan"))
+    dk, dv = dq.clone(), dq.clone()
+    written = {name: torch.zeros(S, H, dtype=torch.int32) for name in ("dq", "dk", "dv")}
+    done_tiles = torch.zeros(P, dtype=torch.int64)
+    for r in range(R):
+        for u in range(U):
+            e = _engine(U, R, u, r)
+            all_segs, mine, tiles_of_me = e._bwd_segments(variant, rows)
+            assert len(all_segs) <= 32
+            assert sorted(x for (_, row0, n, _) in all_segs for x in range(row0, row0 + n)) == list(range(S))
+            hs = slice(u * Hl, (u + 1) * Hl)
+            stage = lambda t: t[:, tok_of_stage][:, :, hs]                            # noqa: E731
+            qs, ks, vs, dos, outs = (stage(t) for t in (q, k, v, do, out))
+            lses = lse[:, hs][:, :, tok_of_stage]
+            spos = torch.empty(S, dtype=torch.int64)
+            for (src, row0, n, pos0) in all_segs:
+                spos[row0:row0 + n] = pos0 + stride * torch.arange(n)
+                assert row0 // rows == src                                              # staging is sp-rank major
+            assert torch.equal(spos, tok_of_stage)                                      # positions == token ids
+            mrows = torch.cat([torch.arange(row0, row0 + n) for (_, row0, n, _) in mine])
+            assert len(mrows) == U * rows and all(src // U == r for (src, _, _, _) in mine)
+            # pass 1: dQ of my ring block (stationary) against everything (streamed)
+            bdq, _, _ = attn_block_bwd_ref(dos[:, mrows], qs[:, mrows], ks, vs, outs[:, mrows], lses[:, :, mrows],
+                                           spos[mrows], spos, p.softmax_scale, True, win)
+            # pass 2: dK/dV of my ring block (stationary) against every query (streamed)
+            _, bdk, bdv = attn_block_bwd_ref(dos, qs, ks[:, mrows], vs[:, mrows], outs, lses, spos, spos[mrows],
+                                             p.softmax_scale, True, win)
+            off = 0
+            for (src, row0, n, pos0) in mine:
+                o_row0 = row0 - src * rows                                              # row inside the owner's shard
+                owner_tok = own[(src % U, src // U)][o_row0:o_row0 + n]
+                assert torch.equal(owner_tok, tok_of_stage[row0:row0 + n])
+                dq[owner_tok, hs] = bdq[0, off:off + n]
+                dk[owner_tok, hs] = bdk[0, off:off + n]
+                dv[owner_tok, hs] = bdv[0, off:off + n]
+                for name in written:
+                    written[name][owner_tok, hs] += 1
+                done_tiles[src] += (n + 127) // 128
+                off += n
+            # what this rank waits for: tiles of its own tokens, produced by the U ranks of its ring block
+            assert tiles_of_me == sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == e.me)
+    for name in written:
+        assert bool((written[name] == 1).all()), name
+    torch.testing.assert_close(dq, rdq[0], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(dk, rdk[0], atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(dv, rdv[0], atol=1e-5, rtol=1e-5)
+    # every owner receives U x (its tile count) completions per pass (one per Ulysses rank of the producing ring block)
+    for src in range(P):
+        e = _engine(U, R, src % U, src // U)
+        assert done_tiles[src] == U * e._bwd_segments(variant, rows)[2]
