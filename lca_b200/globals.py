@@ -60,6 +60,21 @@ class _ProcessGroupState:
 
 PROCESS_GROUP = _ProcessGroupState()
 
+# names the reference exposes from ``yunchang.globals`` (``globals.py:5-24``); code that does
+# ``ProcessGroupSingleton()`` gets the one shared state object, exactly like there.
+ProcessGroupSingleton = _ProcessGroupState
+
+
+class Singleton:
+    """Base for process-wide singletons (``yunchang/globals.py:5-11``)."""
+
+    _instance = None
+
+    def __new__(cls, *args, **kwargs):
+        if cls._instance is None:
+            cls._instance = super().__new__(cls)
+        return cls._instance
+
 
 def set_seq_parallel_pg(
     sp_ulysses_degree: int,
@@ -150,6 +165,16 @@ HAS_AITER = False                                # ROCm only
 HAS_SAGE_ATTENTION = _has("sageattention")
 HAS_SPARSE_SAGE_ATTENTION = _has("spas_sage_attn")
 HAS_NPU = False                                  # Ascend only
+
+
+def get_cuda_arch() -> str:
+    """``"major.minor"`` of the current device (``yunchang/globals.py:102-104``); ``"10.0"`` (the only build target)
+    when no GPU is visible.  Unlike the reference this never touches ``TORCH_CUDA_ARCH_LIST``."""
+    import torch
+    if torch.cuda.is_available():
+        major, minor = torch.cuda.get_device_capability()
+        return f"{major}.{minor}"
+    return "10.0"
 
 
 def has_native_kernels() -> bool:

@@ -89,6 +89,18 @@ def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_pro
     return pytorch_attn_func if torch_like else flash_attn_func
 
 
+# the reference's kernels package also re-exports the feature probes and the torch ring function
+from ..globals import (HAS_AITER, HAS_FLASH_ATTN, HAS_FLASH_ATTN_HOPPER, HAS_FLASHINFER, HAS_NPU,  # noqa: E402,F401
+                       HAS_SAGE_ATTENTION, HAS_SPARSE_SAGE_ATTENTION)
+
+
+def __getattr__(name):          # lazy: lca_b200.ring imports this package
+    if name == "ring_pytorch_attn_func":
+        from ..ring import ring_pytorch_attn_func
+        return ring_pytorch_attn_func
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+
 __all__ = ["AttnType", "select_flash_attn_impl", "flash_attn_forward", "flash_attn_backward", "flash_attn_func",
            "pytorch_attn_forward", "pytorch_attn_backward", "pytorch_attn_func", "flash_attn3_func_forward",
            "flash_attn3_func_backward", "flashinfer_attn_forward", "flashinfer_attn_backbward", "flashinfer_attn_backward",

@@ -269,3 +269,52 @@ def _packed_varlen_worker(rank, world):
 
 def test_varlen_packed_wrappers():
     run_distributed(_packed_varlen_worker, 2)
+
+
+# ------------------------------------------------------------------------------------------ reference-path modules
+def _lowlevel_worker(rank, world):
+    """``from yunchang.ring.<file> import <variant>_forward/_backward`` style entry points (positional reference
+    signatures) against the single-device result, dense and varlen."""
+    from lca_b200.comm.all_to_all import SeqAllToAll4D  # noqa: F401  (module paths of the reference must import)
+    from lca_b200.comm.extract_local import zigzag_extract_local  # noqa: F401
+    from lca_b200.kernels import AttnType
+    from lca_b200.parallel.layout import local_token_index
+    from lca_b200.ring.ring_flash_attn import ring_flash_attn_backward, ring_flash_attn_forward
+    from lca_b200.ring.ring_flash_attn_varlen import ring_flash_attn_varlen_backward, ring_flash_attn_varlen_forward
+    from lca_b200.ring.stripe_flash_attn import stripe_flash_attn_backward, stripe_flash_attn_forward
+    from lca_b200.ring.zigzag_ring_flash_attn import zigzag_ring_flash_attn_backward, zigzag_ring_flash_attn_forward
+    from lca_b200.ring.zigzag_ring_flash_attn_varlen import (get_half_index, zigzag_ring_flash_attn_varlen_backward,
+                                                            zigzag_ring_flash_attn_varlen_forward)
+    B, S, H, D = 1, 16 * world, 2, 8
+    q, k, v, do = _global_inputs(B, S, H, H, D, seed=3)
+    scale = D ** -0.5
+    ro, rdq, rdk, rdv = _reference(q, k, v, do, causal=True)
+    for variant, fwd, bwd in [("basic", ring_flash_attn_forward, ring_flash_attn_backward),
+                              ("zigzag", zigzag_ring_flash_attn_forward, zigzag_ring_flash_attn_backward),
+                              ("stripe", stripe_flash_attn_forward, stripe_flash_attn_backward)]:
+        idx = local_token_index(variant, S, 0, rank, 1, world)
+        lq, lk, lv, ldo = (t[:, idx].contiguous() for t in (q, k, v, do))
+        out, lse = fwd(None, lq, lk, lv, scale, 0, True, (-1, -1), 0.0, None, False, AttnType.TORCH)
+        assert lse.shape == (B, H, S // world)
+        dq, dk, dv = bwd(None, ldo, lq, lk, lv, out, lse, scale, 0, True, (-1, -1), 0.0, None, False, AttnType.TORCH)
+        for got, ref, name in [(out, ro, "out"), (dq, rdq, "dq"), (dk, rdk, "dk"), (dv, rdv, "dv")]:
+            torch.testing.assert_close(got, ref[:, idx], atol=2e-5, rtol=1e-4, msg=f"{variant}:{name}")
+    # varlen: one packed sequence per call keeps the bookkeeping short; cu_seqlens are LOCAL cumulative lengths
+    for variant, fwd, bwd, extra in [
+            ("basic", ring_flash_attn_varlen_forward, ring_flash_attn_varlen_backward, ()),
+            ("zigzag", zigzag_ring_flash_attn_varlen_forward, zigzag_ring_flash_attn_varlen_backward, (None, None))]:
+        idx = local_token_index(variant, S, 0, rank, 1, world)
+        lq, lk, lv, ldo = (t[0, idx].contiguous() for t in (q, k, v, do))
+        cu = torch.tensor([0, S // world], dtype=torch.int32)
+        out, lse = fwd(None, lq, lk, lv, cu, S // world, *extra, scale, 0, True)
+        assert out.shape == lq.shape and lse.shape == (H, S // world)
+        dq, dk, dv = bwd(None, ldo, lq, lk, lv, out, lse, cu, S // world, *extra, scale, 0, True)
+        for got, ref, name in [(out, ro, "out"), (dq, rdq, "dq"), (dk, rdk, "dk"), (dv, rdv, "dv")]:
+            torch.testing.assert_close(got, ref[0, idx], atol=2e-5, rtol=1e-4, msg=f"varlen-{variant}:{name}")
+    hi = get_half_index(torch.tensor([0, 8, 12]), front=False)
+    assert hi.tolist() == [False] * 4 + [True] * 4 + [False] * 2 + [True] * 2
+    assert get_half_index([0, 8], front=True) == slice(None, 4)
+
+
+def test_reference_module_paths_and_lowlevel_ring_functions():
+    run_distributed(_lowlevel_worker, 2)
