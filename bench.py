@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-causal", action="store_true")
     ap.add_argument("--backend", default=None, help="ours: auto|fused|collective")
     ap.add_argument("--window", type=int, default=-1, help="sliding window (left) in tokens; -1 = none (BASELINE config 4)")
+    ap.add_argument("--no-comm-probe", action="store_true",
+                    help="skip the compute-only re-run that yields exposed_comm_ms (ours, N > 1; outside the timed regions)")
     ap.add_argument("--qkvpacked", action="store_true", help="LongContextAttentionQKVPacked (BASELINE config 5; MHA only)")
     return ap.parse_args()
 
@@ -252,6 +254,53 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
+    # ------------------------------------------------------------------ exposed communication (ours, N > 1)
+    # The same tcgen05 kernels on the same per-rank problem (this rank's ring block of queries against all S keys,
+    # its head slice) with every operand already local: no pushes, no arrival flags, no NVLink traffic.  The
+    # difference to the fused step time is the communication the fused kernels failed to hide.
+    comm_probe = None
+    if a.impl == "ours" and world > 1 and not a.no_comm_probe:
+        local_ms = float("nan")
+        try:
+            from lca_b200.ops.attention import AttnParams
+            from lca_b200.parallel.layout import Seg, ring_positions
+            Sr, Hl, Hkvl = U * Sl, H // U, max(Hkv // U, 1)
+            gq = torch.Generator(device=dev).manual_seed(99 + rank)
+            qb = torch.randn(B, Sr, Hl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
+            dob = torch.randn(B, Sr, Hl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
+            kf = torch.randn(B, S, Hkvl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
+            vf = torch.randn(B, S, Hkvl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
+            win = (a.window, 0 if causal else a.window) if a.window >= 0 else (-1, -1)
+            pp = AttnParams.make(qb, None, causal, win)
+            q_pos = ring_positions(a.ring_impl, rank // U, R, Sr)
+            k_pos = (Seg(0, S, 1),)
+
+            def local_step():
+                o, l = native.fmha_fwd(qb, kf, vf, q_pos, k_pos, pp)
+                if need_grad:
+                    native.fmha_bwd(dob, qb, kf, vf, o, l, q_pos, k_pos, pp)
+
+            for _ in range(2):
+                local_step()
+            torch.cuda.synchronize(dev)
+            n_probe = max(1, min(a.steps, 5))
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(n_probe):
+                local_step()
+                flush.fill_(1)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            local_ms = c0.elapsed_time(c1) / n_probe
+            del qb, dob, kf, vf
+        except Exception as e:  # noqa: BLE001 - the probe must never cost the headline number
+            comm_probe = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
+        t = torch.tensor([local_ms if local_ms == local_ms else -1.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if comm_probe is None and float(t[0]) > 0:
+            comm_probe = {"compute_only_ms": round(float(t[0]), 4), "exposed_comm_ms": round(ms - float(t[0]), 4),
+                          "how": "same kernels, same per-rank problem, all operands local (no NVLink); max over ranks"}
+
     flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
     if need_grad:
         flops *= 3.5
@@ -274,6 +323,7 @@ def main():
             "e2e": {"value": round(tflops_e2e, 2), "unit": "TFLOPS", "ms_per_step": round(ms_e2e, 4),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(n_launch * a.steps) if a.impl == "ours" else None,
+            "comm": comm_probe,
         }))
     if need_dist:
         dist.destroy_process_group()
