@@ -23,7 +23,7 @@ from ..globals import PROCESS_GROUP, group_size
 from ..kernels import AttnType
 from ..parallel.all_to_all import SeqAllToAll4D
 from ..parallel.layout import canonical_variant
-from .attn_layer import LongContextAttention, _resolve_backend, _slice_alibi
+from .attn_layer import LongContextAttention, _dropout_kw, _resolve_backend, _slice_alibi
 from .utils import RING_IMPL_DICT
 
 
@@ -100,6 +100,7 @@ class AsyncLongContextAttention(torch.nn.Module):
 
         outs = [None] * n_groups
         out_events = [None] * n_groups
+        dkw = _dropout_kw(dropout_p, self.ulysses_pg, n_groups)     # one seed per call; stage i = global head u*H/U + i
         for i in range(n_groups):
             if use_streams:
                 cur.wait_event(events[i])
@@ -111,7 +112,8 @@ class AsyncLongContextAttention(torch.nn.Module):
                                    window_size=window_size, softcap=softcap,
                                    alibi_slopes=None if alibi is None else alibi[..., i:i + 1].contiguous(),
                                    deterministic=deterministic, return_attn_probs=False, group=self.ring_pg,
-                                   attn_type=self.attn_type)
+                                   attn_type=self.attn_type,
+                                   **(dict(dkw, head_offset=dkw["head_offset"] + i) if dkw else {}))
             if use_streams:
                 done = torch.cuda.Event()
                 done.record(cur)

@@ -54,6 +54,17 @@ def _resolve_backend(requested: Optional[str]) -> str:
     return b
 
 
+def _dropout_kw(dropout_p, ulysses_pg, local_heads: int, stage: int = 0) -> dict:
+    """Extra ring-function arguments when dropout is on: one seed per module call (drawn from torch's CPU generator,
+    so ranks that share ``torch.manual_seed`` share it) and the global index of this rank's first local head --
+    the dropout mask is a function of global coordinates (``ops/dropout.py``), hence identical to a single-device
+    run with the same seed whatever the Ulysses x Ring layout."""
+    if not dropout_p or dropout_p <= 0:
+        return {}
+    seed = int(torch.randint(1, 2**31 - 1, (1,)).item())
+    return dict(dropout_seed=seed, head_offset=group_rank(ulysses_pg) * local_heads + stage)
+
+
 class LongContextAttention(torch.nn.Module):
     """Arguments (same as the reference, plus ``backend``):
         scatter_idx, gather_idx : all-to-all axes (2, 1)
@@ -118,7 +129,8 @@ class LongContextAttention(torch.nn.Module):
         out = self.ring_attn_fn(query_layer, key_layer, value_layer, dropout_p=dropout_p, softmax_scale=softmax_scale,
                                 causal=causal, window_size=window_size, softcap=softcap, alibi_slopes=alibi,
                                 deterministic=deterministic, return_attn_probs=return_attn_probs, group=self.ring_pg,
-                                attn_type=self.attn_type, attn_processor=self.attn_processor)
+                                attn_type=self.attn_type, attn_processor=self.attn_processor,
+                                **_dropout_kw(dropout_p, self.ulysses_pg, query_layer.shape[2]))
         context_layer = out[0] if isinstance(out, tuple) else out
         # (B, S/R, H/U, D) -> (B, S/P, H, D)
         return SeqAllToAll4D.apply(self.ulysses_pg, context_layer, self.gather_idx, self.scatter_idx, self.use_sync)
@@ -162,7 +174,8 @@ class LongContextAttentionQKVPacked(torch.nn.Module):
         out = self.ring_attn_fn(qkv, dropout_p=dropout_p, softmax_scale=softmax_scale, causal=causal,
                                 window_size=window_size, softcap=softcap,
                                 alibi_slopes=_slice_alibi(alibi_slopes, self.ulysses_pg), deterministic=deterministic,
-                                return_attn_probs=return_attn_probs, group=self.ring_pg, attn_type=self.attn_type)
+                                return_attn_probs=return_attn_probs, group=self.ring_pg, attn_type=self.attn_type,
+                                **_dropout_kw(dropout_p, self.ulysses_pg, qkv.shape[3]))
         out = out[0] if isinstance(out, tuple) else out
         if U > 1:
             out = SeqAllToAll4D.apply(self.ulysses_pg, out, self.gather_idx, self.scatter_idx - 1, self.use_sync)

@@ -12,6 +12,8 @@ These whole-sequence wrappers assume positions ``0..S-1`` (bottom-right aligned 
 """
 from __future__ import annotations
 
+from dataclasses import replace
+
 import torch
 
 from ..ops.attention import AttnParams, attn_block_bwd, attn_block_fwd
@@ -23,18 +25,29 @@ def _pos(q, k):
     return (Seg(max(Sk - Sq, 0), Sq, 1),), (Seg(0, Sk, 1),)
 
 
+def _with_dropout(p: AttnParams, dropout_seed, head_offset) -> AttnParams:
+    """Dropout masks are functions of (seed, batch, head, positions) (``ops/dropout.py``): a forward / backward pair
+    must be given the same ``dropout_seed`` (default 0) -- there is no RNG state to carry."""
+    if p.dropout_p <= 0.0:
+        return p
+    return replace(p, dropout_seed=int(dropout_seed or 0), head_offset=int(head_offset or 0))
+
+
 def _fwd(engine, q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
-         alibi_slopes=None, return_softmax=False, op_type=None):
-    if dropout_p and dropout_p > 0:
-        raise NotImplementedError("dropout is only available through the ring/ulysses autograd functions")
-    p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes)
+         alibi_slopes=None, return_softmax=False, op_type=None, dropout_seed=0, head_offset=0):
+    p = _with_dropout(AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p),
+                      dropout_seed, head_offset)
     qp, kp = _pos(q, k)
     return attn_block_fwd(q, k, v, qp, kp, p, engine)
 
 
 def _bwd(engine, dout, q, k, v, out, softmax_lse, dq=None, dk=None, dv=None, dropout_p=0.0, softmax_scale=None,
-         causal=False, window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, rng_state=None):
-    p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, 0.0, deterministic)
+         causal=False, window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, rng_state=None,
+         dropout_seed=None, head_offset=0):
+    if dropout_seed is None:          # the reference threads flash-attn's rng_state here; an int seed is accepted too
+        dropout_seed = rng_state if isinstance(rng_state, int) else 0
+    p = _with_dropout(AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p,
+                                      deterministic), dropout_seed, head_offset)
     qp, kp = _pos(q, k)
     gq, gk, gv = attn_block_bwd(dout, q, k, v, out, softmax_lse, qp, kp, p, engine)
     if dq is not None:
@@ -80,10 +93,12 @@ class _LocalAttnFunc(torch.autograd.Function):
 
 
 def _func(engine, q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
-          alibi_slopes=None, deterministic=False, return_attn_probs=False):
-    if dropout_p and dropout_p > 0:
-        raise NotImplementedError("use UlyssesAttention / ring functions for dropout")
-    p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, 0.0, deterministic)
+          alibi_slopes=None, deterministic=False, return_attn_probs=False, dropout_seed=None, head_offset=0):
+    p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
+    if p.dropout_p > 0.0:
+        if dropout_seed is None:      # torch's CPU generator: torch.manual_seed() makes the masks reproducible
+            dropout_seed = int(torch.randint(1, 2**31 - 1, (1,)).item())
+        p = _with_dropout(p, dropout_seed, head_offset)
     if return_attn_probs:
         out, lse = _LocalAttnFunc.apply(q, k, v, p, engine, True)
         return out, lse, None

@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 import torch
 
 from ..parallel.layout import PosSpec, group_tensor, has_groups, pos_min_max, pos_tensor
-from . import native, ref_attention
+from . import dropout, native, ref_attention
 
 
 @dataclass(frozen=True)
@@ -33,6 +33,8 @@ class AttnParams:
     alibi_slopes: Optional[torch.Tensor] = None
     dropout_p: float = 0.0
     deterministic: bool = False
+    dropout_seed: int = 0          # dropout is a pure function of (seed, batch, head, q position, k position): ops/dropout.py
+    head_offset: int = 0           # global index of local head 0 (Ulysses head shards), part of the dropout key
 
     @staticmethod
     def make(q, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
@@ -96,6 +98,16 @@ def _warn_once(msg: str) -> None:
         warnings.warn(msg, stacklevel=3)
 
 
+def _dropout_args(p: AttnParams, B, H, qpt, kpt, q_grp, dropout_mask):
+    """-> (effective drop probability, keep mask) for the PyTorch engine; the mask is regenerated from the global
+    coordinates unless the caller supplies one (oracle tests)."""
+    if p.dropout_p <= 0.0:
+        return 0.0, None
+    if dropout_mask is None:
+        dropout_mask = dropout.keep_mask(p.dropout_seed, B, H, qpt, kpt, p.dropout_p, p.head_offset, 0, q_grp)
+    return dropout.p_eff(p.dropout_p), dropout_mask
+
+
 def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
                    engine: Optional[str] = None, dropout_mask=None):
     """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32."""
@@ -103,11 +115,12 @@ def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
     if eng == "native" and p.dropout_p == 0.0:
         return native.fmha_fwd(q, k, v, q_pos, k_pos, p)
     grp = has_groups(q_pos) or has_groups(k_pos)
+    qpt, kpt = pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device)
+    q_grp = group_tensor(q_pos, q.device) if grp else None
+    pe, dm = _dropout_args(p, q.shape[0], q.shape[2], qpt, kpt, q_grp, dropout_mask)
     return ref_attention.attn_block_fwd_ref(
-        q, k, v, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device), p.softmax_scale,
-        p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p, dropout_mask,
-        q_grp=group_tensor(q_pos, q.device) if grp else None,
-        k_grp=group_tensor(k_pos, q.device) if grp else None)
+        q, k, v, qpt, kpt, p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, pe, dm,
+        q_grp=q_grp, k_grp=group_tensor(k_pos, q.device) if grp else None)
 
 
 def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
@@ -131,12 +144,13 @@ def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: A
         dk.add_(gk) if acc_dkv else dk.copy_(gk)
         dv.add_(gv) if acc_dkv else dv.copy_(gv)
         return dq, dk, dv
+    grp = has_groups(q_pos) or has_groups(k_pos)
+    qpt, kpt = pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device)
+    q_grp = group_tensor(q_pos, q.device) if grp else None
+    pe, dm = _dropout_args(p, q.shape[0], q.shape[2], qpt, kpt, q_grp, dropout_mask)
     return ref_attention.attn_block_bwd_ref(
-        dout, q, k, v, out, lse, pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device),
-        p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, p.dropout_p,
-        dropout_mask, delta=delta,
-        q_grp=group_tensor(q_pos, q.device) if (has_groups(q_pos) or has_groups(k_pos)) else None,
-        k_grp=group_tensor(k_pos, q.device) if (has_groups(q_pos) or has_groups(k_pos)) else None)
+        dout, q, k, v, out, lse, qpt, kpt, p.softmax_scale, p.causal, p.window_size, p.softcap, p.alibi_slopes, pe,
+        dm, delta=delta, q_grp=q_grp, k_grp=group_tensor(k_pos, q.device) if grp else None)
 
 
 # ------------------------------------------------------------------------------------------

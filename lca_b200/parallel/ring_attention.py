@@ -15,6 +15,7 @@ The zigzag/stripe load balance is preserved because the kernel skips fully maske
 """
 from __future__ import annotations
 
+from dataclasses import replace
 from typing import Optional
 
 import torch
@@ -37,14 +38,6 @@ def _engine_for(attn_type) -> Optional[str]:
     return None
 
 
-def _dropout_mask(seed: int, rank: int, src: int, B, H, Sq, Sk, p_drop, device):
-    if p_drop <= 0.0:
-        return None
-    g = torch.Generator(device=device)
-    g.manual_seed((seed * 1000003 + rank * 8191 + src) & 0x7FFFFFFFFFFF)
-    return torch.rand((B, H, Sq, Sk), generator=g, device=device) >= p_drop
-
-
 def _pos_builders(variant, R, Lq, Lk, cu_seqlens_q=None, cu_seqlens_k=None):
     """-> (qpos(rank), kpos(rank)) closures; dense shards or packed varlen shards."""
     if cu_seqlens_q is None:
@@ -63,9 +56,10 @@ def ring_attn_forward(group, q, k, v, variant: str, p: AttnParams, engine=None, 
     Lk = k.shape[1]
     qpos_of, kpos_of = _pos_builders(variant, R, Lq, Lk, cu_seqlens_q, cu_seqlens_k)
     q_pos = qpos_of(r)
+    if p.dropout_p > 0.0 and dropout_seed:
+        p = replace(p, dropout_seed=int(dropout_seed))       # masks are functions of global coordinates (ops/dropout.py)
     if R == 1:
-        dm = _dropout_mask(dropout_seed, r, r, B, H, Lq, Lk, p.dropout_p, q.device)
-        return attn_block_fwd(q, k, v, q_pos, kpos_of(0), p, engine, dm)
+        return attn_block_fwd(q, k, v, q_pos, kpos_of(0), p, engine)
     comm = RingComm(group)
     k, v = k.contiguous(), v.contiguous()      # P2P payloads must be dense (packed-QKV views are not)
     out_acc = lse_acc = None
@@ -77,8 +71,7 @@ def ring_attn_forward(group, q, k, v, variant: str, p: AttnParams, engine=None, 
         src = (r - step) % R
         k_pos = kpos_of(src)
         if block_is_visible(q_pos, k_pos, p):
-            dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
-            bo, bl = attn_block_fwd(q, k, v, q_pos, k_pos, p, engine, dm)
+            bo, bl = attn_block_fwd(q, k, v, q_pos, k_pos, p, engine)
             if out_acc is None:
                 out_acc, lse_acc = bo.to(torch.float32), bl
             else:
@@ -106,9 +99,10 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
         delta, lse2 = native.attn_delta(out, dout, lse)     # one fused pass: rowsum(dO o O) + log2-domain LSE
     else:
         delta = (dout.to(torch.float32) * out.to(torch.float32)).sum(-1).permute(0, 2, 1).contiguous()
+    if p.dropout_p > 0.0 and dropout_seed:
+        p = replace(p, dropout_seed=int(dropout_seed))
     if R == 1:
-        dm = _dropout_mask(dropout_seed, r, r, B, H, Lq, Lk, p.dropout_p, q.device)
-        dq, dk, dv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, kpos_of(0), p, engine, dm, delta, lse2)
+        dq, dk, dv = attn_block_bwd(dout, q, k, v, out, lse, q_pos, kpos_of(0), p, engine, None, delta, lse2)
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype)
     kv_comm, dkv_comm = RingComm(group), RingComm(group)
     k, v = k.contiguous(), v.contiguous()
@@ -126,11 +120,10 @@ def ring_attn_backward(group, dout, q, k, v, out, lse, variant: str, p: AttnPara
             dkv_comm.wait()                       # partial dK/dV of the block we now hold (from the previous rank)
             dk_acc, dv_acc = next_dk, next_dv
         if block_is_visible(q_pos, k_pos, p):
-            dm = _dropout_mask(dropout_seed, r, src, B, H, Lq, Lk, p.dropout_p, q.device)
             if step == 0:
                 dk_acc, dv_acc = torch.empty(k.shape, **f32), torch.empty(v.shape, **f32)
             # the kernels write / accumulate straight into the fp32 buffers (no extra passes)
-            attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, dm, delta, lse2,
+            attn_block_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, engine, None, delta, lse2,
                            into=(dq, dk_acc, dv_acc, dq_live, step > 0))
             dq_live = True
         elif step == 0:
@@ -152,10 +145,15 @@ class RingAttnFunc(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, variant, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
-                deterministic, return_softmax, group, attn_type, attn_processor):
+                deterministic, return_softmax, group, attn_type, attn_processor, head_offset=0, dropout_seed=None):
         p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
         engine = _engine_for(attn_type)
-        seed = int(torch.randint(0, 2**31 - 1, (1,)).item()) if p.dropout_p > 0 else 0
+        seed = 0
+        if p.dropout_p > 0:
+            # drawn from torch's CPU generator: ranks that share torch.manual_seed() share the dropout seed, which
+            # makes a sequence-parallel run reproduce the single-device masks exactly (ops/dropout.py)
+            seed = int(dropout_seed) if dropout_seed is not None else int(torch.randint(1, 2**31 - 1, (1,)).item())
+            p = replace(p, head_offset=int(head_offset))
         out, lse = ring_attn_forward(group, q, k, v, variant, p, engine, seed)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.p, ctx.variant, ctx.group, ctx.engine, ctx.seed = p, variant, group, engine, seed
@@ -168,7 +166,7 @@ class RingAttnFunc(torch.autograd.Function):
     def backward(ctx, dout, *args):
         q, k, v, out, lse = ctx.saved_tensors
         dq, dk, dv = ring_attn_backward(ctx.group, dout, q, k, v, out, lse, ctx.variant, ctx.p, ctx.engine, ctx.seed)
-        return (dq, dk, dv) + (None,) * 12
+        return (dq, dk, dv) + (None,) * 14
 
 
 def _make_funcs(variant: str):
@@ -176,21 +174,22 @@ def _make_funcs(variant: str):
 
     def func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
              alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
-             attn_processor=None):
+             attn_processor=None, head_offset=0, dropout_seed=None):
         return RingAttnFunc.apply(q, k, v, variant, dropout_p, softmax_scale, causal, window_size, softcap,
-                                  alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+                                  alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor,
+                                  head_offset, dropout_seed)
 
     def kvpacked(q, kv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
                  alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
-                 attn_processor=None):
+                 attn_processor=None, **kw):
         return func(q, kv[:, :, 0], kv[:, :, 1], dropout_p, softmax_scale, causal, window_size, softcap,
-                    alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+                    alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor, **kw)
 
     def qkvpacked(qkv, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
                   alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
-                  attn_processor=None):
+                  attn_processor=None, **kw):
         return func(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], dropout_p, softmax_scale, causal, window_size,
-                    softcap, alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor)
+                    softcap, alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor, **kw)
 
     return func, kvpacked, qkvpacked
 

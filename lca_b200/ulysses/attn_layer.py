@@ -13,6 +13,7 @@ from typing import Any, Optional
 import torch
 from torch import Tensor
 
+from ..globals import group_rank
 from ..kernels import AttnType, select_flash_attn_impl
 from ..parallel.all_to_all import SeqAllToAll4D
 from ..hybrid.attn_layer import _resolve_backend, _slice_alibi
@@ -53,16 +54,14 @@ class UlyssesAttention(torch.nn.Module):
         v = SeqAllToAll4D.apply(self.spg, value, self.scatter_idx, self.gather_idx, self.use_sync)
         if softmax_scale is None:
             softmax_scale = q.shape[-1] ** -0.5
+        kw = {}
         if dropout_p and dropout_p > 0:
-            from ..parallel.ring_attention import ring_flash_attn_func
-            ctx = ring_flash_attn_func(q, k, v, dropout_p, softmax_scale, causal, window_size, softcap,
-                                       _slice_alibi(alibi_slopes, self.spg), deterministic, False, None,
-                                       self.attn_type)
-        else:
-            ctx = self.attn_fn(q, k, v, dropout_p=0.0, softmax_scale=softmax_scale, causal=causal,
-                               window_size=window_size, softcap=softcap,
-                               alibi_slopes=_slice_alibi(alibi_slopes, self.spg), deterministic=deterministic,
-                               return_attn_probs=return_attn_probs)
+            # the dropout key uses GLOBAL head indices, so the head shard of this rank needs its offset
+            kw = dict(head_offset=group_rank(self.spg) * q.shape[2])
+        ctx = self.attn_fn(q, k, v, dropout_p=dropout_p, softmax_scale=softmax_scale, causal=causal,
+                           window_size=window_size, softcap=softcap,
+                           alibi_slopes=_slice_alibi(alibi_slopes, self.spg), deterministic=deterministic,
+                           return_attn_probs=return_attn_probs, **kw)
         if isinstance(ctx, tuple):
             ctx = ctx[0]
         return SeqAllToAll4D.apply(self.spg, ctx, self.gather_idx, self.scatter_idx, self.use_sync)

@@ -60,7 +60,9 @@ def _hybrid_worker(rank, world, U, R, variant, kw, module, H, Hkv):
     from lca_b200.kernels import AttnType
     B, S, D = 1, 16 * world, 8
     q, k, v, do = _global_inputs(B, S, H, Hkv, D, seed=1)
+    torch.manual_seed(4242)              # dropout seeds are drawn from torch's generator: same draw on every rank
     ro, rdq, rdk, rdv = _reference(q, k, v, do, **kw)
+    torch.manual_seed(4242)
     set_seq_parallel_pg(U, R, rank, world)
     ex = EXTRACT_FUNC_DICT[variant]
     sh = lambda t: ex(t, rank, world, rd=R, ud=U).detach().clone()
@@ -103,6 +105,25 @@ CAUSAL = dict(causal=True)
     (4, 1, "basic", CAUSAL, "ulysses", 8, 4),
 ])
 def test_usp_modules_match_single_device(U, R, variant, kw, module, H, Hkv):
+    run_distributed(_hybrid_worker, U * R, U, R, variant, kw, module, H, Hkv)
+
+
+DROP = dict(causal=True, dropout_p=0.25)
+
+
+@pytest.mark.parametrize("U,R,variant,kw,module,H,Hkv", [
+    (1, 2, "basic", DROP, "hybrid", 4, 4),
+    (1, 4, "zigzag", DROP, "hybrid", 4, 2),
+    (2, 2, "strip", DROP, "hybrid", 4, 4),
+    (2, 2, "zigzag", dict(causal=False, dropout_p=0.5, window_size=(9, 9)), "hybrid", 4, 2),
+    (2, 2, "zigzag", DROP, "qkvpacked", 4, 4),
+    (2, 2, "zigzag", DROP, "async", 4, 2),
+    (4, 1, "basic", DROP, "ulysses", 8, 4),
+])
+def test_usp_dropout_equals_single_device_dropout(U, R, variant, kw, module, H, Hkv):
+    """Dropout masks are functions of (seed, batch, global head, global q/k position): with the same seed every
+    Ulysses x Ring layout reproduces the single-device result exactly, forward and backward (the reference draws an
+    unrelated Philox stream per ring step and cannot re-create its masks in the ring backward)."""
     run_distributed(_hybrid_worker, U * R, U, R, variant, kw, module, H, Hkv)
 
 

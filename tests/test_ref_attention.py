@@ -160,3 +160,49 @@ def test_api_surface_matches_reference_names():
     from lca_b200.comm import SeqAllToAll4D, SeqAllToAll5D, all_to_all_4D, all_to_all_5D   # noqa: F401
     from lca_b200.ring.utils import RingComm, update_out_and_lse, flatten_varlen_lse, unflatten_varlen_lse  # noqa: F401
     from lca_b200.globals import PROCESS_GROUP, HAS_FLASH_ATTN, HAS_FLASH_ATTN_HOPPER, HAS_FLASHINFER, HAS_NPU  # noqa: F401
+
+
+# ------------------------------------------------------------------------------------------ dropout specification
+def test_dropout_mask_statistics_and_keying():
+    from lca_b200.ops import dropout as d
+    assert d.p8_of(0.0) == 0 and d.p8_of(0.1) == 26 and d.p8_of(1.0) == 255
+    assert abs(d.keep_scale(0.25) - 1.0 / 0.75) < 1e-12
+    qp, kp = torch.arange(256), torch.arange(1024)
+    m = d.keep_mask(7, 2, 3, qp, kp, 0.3)
+    assert m.shape == (2, 3, 256, 1024)
+    assert abs(m.float().mean().item() - (1 - d.p_eff(0.3))) < 5e-3
+    f = m.float() - m.float().mean()
+    for a, b in [(f[..., :-1], f[..., 1:]), (f[:, :, :-1], f[:, :, 1:]), (f[:, :-1], f[:, 1:]), (f[:1], f[1:])]:
+        assert abs((a * b).mean().item()) < 3e-3                     # neighbours in k, q, head, batch are uncorrelated
+    # pure function of the GLOBAL coordinates: any sub-block, any order, any head shard reproduces the same bits
+    sub = d.keep_mask(7, 2, 1, qp[64:128], kp[512:700], 0.3, head_offset=2)
+    assert torch.equal(sub[:, 0], m[:, 2, 64:128, 512:700])
+    perm = torch.randperm(1024, generator=torch.Generator().manual_seed(0))
+    assert torch.equal(d.keep_mask(7, 2, 3, qp, kp[perm], 0.3), m[..., perm])
+    assert not torch.equal(d.keep_mask(8, 2, 3, qp, kp, 0.3), m)     # the seed matters
+    assert bool(d.keep_mask(7, 1, 1, qp, kp, 0.0).all())
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_single_device_dropout_matches_autograd_of_dense_formula(causal):
+    """``flash_attn_func(dropout_p>0)`` (the reference's single-device entry point raised here before): forward and the
+    hand-written backward against autograd through softmax -> mask -> rescale -> @V with the same keep mask."""
+    from lca_b200.kernels.attention import pytorch_attn_func
+    from lca_b200.ops import dropout as d
+    B, S, H, D, pd, seed = 2, 40, 3, 8, 0.4, 99
+    g = torch.Generator().manual_seed(3)
+    q, k, v, do = (torch.randn(B, S, H, D, generator=g, dtype=torch.float64) for _ in range(4))
+    q1, k1, v1 = (t.clone().requires_grad_() for t in (q, k, v))
+    out = pytorch_attn_func(q1, k1, v1, dropout_p=pd, causal=causal, dropout_seed=seed)
+    out.backward(do)
+    q2, k2, v2 = (t.clone().requires_grad_() for t in (q, k, v))
+    s = torch.einsum("bqhd,bkhd->bhqk", q2, k2) * D ** -0.5
+    if causal:
+        s = s.masked_fill(torch.ones(S, S, dtype=torch.bool).triu(1), float("-inf"))
+    keep = d.keep_mask(seed, B, H, torch.arange(S), torch.arange(S), pd)
+    pr = torch.softmax(s, dim=-1) * keep * d.keep_scale(pd)
+    ref = torch.einsum("bhqk,bkhd->bqhd", pr, v2)
+    ref.backward(do)
+    torch.testing.assert_close(out, ref, atol=1e-5, rtol=1e-4)          # the engine computes in fp32
+    for a, b in [(q1.grad, q2.grad), (k1.grad, k2.grad), (v1.grad, v2.grad)]:
+        torch.testing.assert_close(a, b, atol=1e-5, rtol=1e-4)
