@@ -112,7 +112,7 @@ def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
                    engine: Optional[str] = None, dropout_mask=None):
     """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32."""
     eng = pick_engine(q, engine)
-    if eng == "native" and p.dropout_p == 0.0:
+    if eng == "native" and (p.dropout_p == 0.0 or (dropout_mask is None and native.dropout_supported(p))):
         return native.fmha_fwd(q, k, v, q_pos, k_pos, p)
     grp = has_groups(q_pos) or has_groups(k_pos)
     qpt, kpt = pos_tensor(q_pos, q.device), pos_tensor(k_pos, q.device)
@@ -131,7 +131,8 @@ def attn_block_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p: A
     (``acc_*`` True); the native kernels do the ``+=`` in their epilogue, so a ring step costs no
     extra pass over the gradients."""
     eng = pick_engine(q, engine)
-    if eng == "native" and p.dropout_p == 0.0 and native.has_bwd():
+    if eng == "native" and native.has_bwd() and (p.dropout_p == 0.0 or
+                                                  (dropout_mask is None and native.dropout_supported(p))):
         if into is not None:
             dq, dk, dv, acc_dq, acc_dkv = into
             return native.fmha_bwd(dout, q, k, v, out, lse, q_pos, k_pos, p, delta=delta, lse2=lse2, dq=dq, dk=dk,

@@ -233,20 +233,51 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   p.lse_own_sh = out.size(1);
 }
 
+// drop = {} (no dropout) or {p8, seed, global index of local query head 0}: EXPERIMENTAL dropout instantiations
+template <typename P>
+static void set_dropout(P& p, const std::vector<int64_t>& drop, double softcap) {
+  if (drop.empty() || drop[0] <= 0) return;
+  TORCH_CHECK(drop.size() == 3 && drop[0] < 256, "drop = {p8, seed, head_offset}");
+  TORCH_CHECK(softcap == 0.0, "native dropout does not combine with softcap (use the PyTorch engine)");
+  p.drop_p8 = static_cast<int>(drop[0]);
+  p.drop_seed = static_cast<uint32_t>(drop[1] & 0xFFFFFFFFll);
+  p.drop_rscale = 256.0f / static_cast<float>(256 - p.drop_p8);
+  p.drop_head_off = static_cast<int>(drop[2]);
+}
+
+static void fmha_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                          const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
+                          int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
+                          double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
+                          int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit, const std::vector<int64_t>& drop) {
+  c10::cuda::CUDAGuard guard(q.device());
+  FwdParams p;
+  fill_fwd_params(p, q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap,
+                  alibi, flags_ptr, flag_epoch);
+  set_dropout(p, drop, softcap);
+  int sms = num_sms();
+  if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  if (p.drop_p8 == 0) attach_sched(p, q, sms, 0);     // the dropout instantiations use the static schedule
+  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
+                              at::cuda::getCurrentCUDAStream()));
+}
+
 void fmha_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
               const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
               int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
               double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
               int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit) {
-  c10::cuda::CUDAGuard guard(q.device());
-  FwdParams p;
-  fill_fwd_params(p, q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap,
-                  alibi, flags_ptr, flag_epoch);
-  int sms = num_sms();
-  if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
-  attach_sched(p, q, sms, 0);
-  LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
-                              at::cuda::getCurrentCUDAStream()));
+  fmha_fwd_impl(q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap, alibi,
+                flags_ptr, flag_epoch, sm_limit, {});
+}
+
+void fmha_fwd_drop(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                   const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
+                   int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
+                   double scale, int64_t wl, int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi,
+                   int64_t flags_ptr, int64_t flag_epoch, int64_t sm_limit, const std::vector<int64_t>& drop) {
+  fmha_fwd_impl(q, k, v, qsegs, ksegs, q_pos_stride, k_pos_stride, out, o_head_off, lse, scale, wl, wr, softcap, alibi,
+                flags_ptr, flag_epoch, sm_limit, drop);
 }
 
 // mesh = {P, U, R, u, r, rows, n_comm};  qlike/kvlike: user shards to push with their destination byte offsets.
@@ -507,11 +538,13 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   p.out_mode = static_cast<int>(out_mode);
 }
 
-void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
+static void fmha_bwd_pass_impl(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
+                   const at::Tensor& y1,
                    const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
                    int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
                    at::Tensor& out0, const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl,
-                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit) {
+                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit,
+                   const std::vector<int64_t>& drop) {
   c10::cuda::CUDAGuard guard(x0.device());
   BwdParams p;
   const bool f32 = out0.scalar_type() == at::kFloat;
@@ -519,11 +552,32 @@ void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, cons
   TORCH_CHECK(out0.size(2) == x0.size(2), "out heads");
   fill_bwd_params(p, is_dkv, x0, x1, y0, y1, xsegs, ysegs, x_pos_stride, y_pos_stride, lse2, delta, out0, out1,
                   f32 ? (accumulate ? 2 : 1) : 0, scale, wl, wr, softcap, alibi);
+  set_dropout(p, drop, softcap);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
-  attach_sched(p, x0, sms, 0);
+  if (p.drop_p8 == 0) attach_sched(p, x0, sms, 0);
   LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, sms,
                               at::cuda::getCurrentCUDAStream()));
+}
+
+void fmha_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0, const at::Tensor& y1,
+                   const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+                   int64_t x_pos_stride, int64_t y_pos_stride, const at::Tensor& lse2, const at::Tensor& delta,
+                   at::Tensor& out0, const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl,
+                   int64_t wr, double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit) {
+  fmha_bwd_pass_impl(is_dkv, x0, x1, y0, y1, xsegs, ysegs, x_pos_stride, y_pos_stride, lse2, delta, out0, out1, accumulate,
+                     scale, wl, wr, softcap, alibi, sm_limit, {});
+}
+
+void fmha_bwd_pass_drop(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
+                        const at::Tensor& y1, const std::vector<std::vector<int64_t>>& xsegs,
+                        const std::vector<std::vector<int64_t>>& ysegs, int64_t x_pos_stride, int64_t y_pos_stride,
+                        const at::Tensor& lse2, const at::Tensor& delta, at::Tensor& out0,
+                        const c10::optional<at::Tensor>& out1, bool accumulate, double scale, int64_t wl, int64_t wr,
+                        double softcap, const c10::optional<at::Tensor>& alibi, int64_t sm_limit,
+                        const std::vector<int64_t>& drop) {
+  fmha_bwd_pass_impl(is_dkv, x0, x1, y0, y1, xsegs, ysegs, x_pos_stride, y_pos_stride, lse2, delta, out0, out1, accumulate,
+                     scale, wl, wr, softcap, alibi, sm_limit, drop);
 }
 
 // Fused USP backward pass.  dQ pass (is_dkv = false) carries the push CTAs (q, dO | k, v | delta) and scatters dQ tiles
@@ -671,6 +725,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
+  m.def("fmha_fwd_drop", &lca::fmha_fwd_drop, "EXPERIMENTAL: forward with coordinate-keyed dropout");
+  m.def("fmha_bwd_pass_drop", &lca::fmha_bwd_pass_drop, "EXPERIMENTAL: backward pass with coordinate-keyed dropout");
   m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");
   m.def("finalize_out", &lca::finalize_out, "fp32 accumulator -> 16-bit output");
   m.def("flatten_varlen_lse", &lca::flatten_varlen_lse);

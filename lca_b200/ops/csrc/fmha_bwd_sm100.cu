@@ -176,7 +176,7 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 }  // namespace
 
 // kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
@@ -519,7 +519,30 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
               for (int e = 0; e < 4; ++e) { l2v[e] = kPk ? -lse2_r : lse2_r; dlv[e] = kPk ? -delta_r : delta_r; }
             }
             float pv[4], dv[4];
-            if constexpr (kPk) {
+            if constexpr (kDrop) {
+              // dS = P o (keep * dP / (1-p) - delta); the dV GEMM consumes P_drop = keep * P / (1-p).  The keep bits
+              // are regenerated from the global coordinates (ops/dropout.py).  Rows are queries in the dQ pass
+              // (columns = keys: four consecutive keys share a hash word) and keys in the dK/dV pass (columns =
+              // queries: one hash per score).
+              float pd[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int col = half * 32 + c + e;
+                const uint32_t ypos = static_cast<uint32_t>(it.ypos0 + col * p.y_pos_stride);
+                const uint32_t qp = kIsDKV ? ypos : static_cast<uint32_t>(xpos);
+                const uint32_t kp = kIsDKV ? static_cast<uint32_t>(xpos) : ypos;
+                const uint32_t w = ptx::dropout_word(
+                    ptx::dropout_row_key(qp, p.drop_seed, static_cast<uint32_t>(wk.b + p.xseg[wk.xseg].group),
+                                         static_cast<uint32_t>(hq + p.drop_head_off)), kp);
+                const bool keep = ptx::dropout_keep(w, kp, static_cast<uint32_t>(p.drop_p8));
+                pv[e] = ex2(fmaf(__uint_as_float(t0[c + e]), mul, -l2v[e]));
+                dv[e] = pv[e] * ((keep ? __uint_as_float(t1[c + e]) * p.drop_rscale : 0.f) - dlv[e]);
+                pd[e] = keep ? pv[e] * p.drop_rscale : 0.f;
+              }
+              if constexpr (kIsDKV) {
+                pv[0] = pd[0]; pv[1] = pd[1]; pv[2] = pd[2]; pv[3] = pd[3];
+              }
+            } else if constexpr (kPk) {
               // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair (experimental, LCA_B200_F32X2=1)
               // l2v / dlv hold the NEGATED statistics in this variant: x = T0*mul + (-lse2), d = T1 + (-delta)
               const uint64_t mul2 = ptx::pack_f32x2(mul, mul);
@@ -622,10 +645,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -642,6 +665,9 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
+  if (p.drop_p8 > 0)                  // experimental dropout variant (static schedule, scalar arithmetic)
+    return is_dkv ? launch_impl<kD, kBf16, true, false, false, true>(p, num_sms, stream)
+                  : launch_impl<kD, kBf16, false, false, false, true>(p, num_sms, stream);
   if (p.f32x2 && !p.dyn_sched)        // experimental packed element-wise stage (static schedule only)
     return is_dkv ? launch_impl<kD, kBf16, true, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, true>(p, num_sms, stream);

@@ -146,10 +146,11 @@ struct Bars {
 
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
 // kDyn: work items are claimed from a global atomic counter by the producer warp and broadcast to the other roles
+// kDrop: attention dropout regenerated from global coordinates (sm100_ptx.cuh: dropout_*; experimental, opt-in)
 // kPk: the unmasked softmax runs on packed fp32x2 instructions (FFMA2 / FADD2): scale-and-subtract, the polynomial
 //      exp2 and the row sum issue once per element pair (experimental, opt-in: LCA_B200_F32X2=1)
 //       through a 2-deep smem ring (EXPERIMENTAL); otherwise the static snake schedule is used.
-template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk>
+template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
@@ -455,7 +456,40 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         const float sub = (m == -INFINITY) ? 0.f : m;
         // ---- P = exp2(x*mul - m), row sum, pack, store over S
         float rs = 0.f;
-        if (general) {
+        if constexpr (kDrop) {
+          // P = exp2(.), row sum over the UNdropped probabilities, then zero the dropped scores before they feed PV;
+          // the 1/(1-p) rescale is folded into the final normalisation.  One hash word covers four key positions.
+          const uint32_t rkey = ptx::dropout_row_key(static_cast<uint32_t>(qpos), p.drop_seed,
+                                                     static_cast<uint32_t>(wk.b + p.qseg[wk.qseg].group),
+                                                     static_cast<uint32_t>(wk.h + p.drop_head_off));
+          const uint32_t p8 = static_cast<uint32_t>(p.drop_p8);
+          if (p.k_pos_stride == 1 && (it.kpos0 & 3) == 0) {
+#pragma unroll
+            for (int c = 0; c < 128; c += 4) {
+              const uint32_t w = ptx::dropout_word(rkey, static_cast<uint32_t>(it.kpos0 + c));
+              float e[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) e[i] = ex2(fmaf(__uint_as_float(v[c + i]), mul, -sub));
+              rs += (e[0] + e[1]) + (e[2] + e[3]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) e[i] = (((w >> (8 * i)) & 0xFFu) >= p8) ? e[i] : 0.f;
+              v[c >> 1] = pack2<kBf16>(e[0], e[1]);
+              v[(c >> 1) + 1] = pack2<kBf16>(e[2], e[3]);
+            }
+          } else {        // strided (stripe) or unaligned segments: one hash per score
+#pragma unroll
+            for (int c = 0; c < 128; c += 2) {
+              const uint32_t k0 = static_cast<uint32_t>(it.kpos0 + c * p.k_pos_stride);
+              const uint32_t k1 = static_cast<uint32_t>(it.kpos0 + (c + 1) * p.k_pos_stride);
+              float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
+              float p1 = ex2(fmaf(__uint_as_float(v[c + 1]), mul, -sub));
+              rs += p0 + p1;
+              p0 = ptx::dropout_keep(ptx::dropout_word(rkey, k0), k0, p8) ? p0 : 0.f;
+              p1 = ptx::dropout_keep(ptx::dropout_word(rkey, k1), k1, p8) ? p1 : 0.f;
+              v[c >> 1] = pack2<kBf16>(p0, p1);
+            }
+          }
+        } else if (general) {
           if constexpr (kPk) {
             const uint64_t mul2 = ptx::pack_f32x2(mul, mul), nsub2 = ptx::pack_f32x2(-sub, -sub);
             uint64_t acc_a = ptx::pack_f32x2(0.f, 0.f), acc_b = acc_a;
@@ -541,7 +575,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         mbar_wait(B.q_full[t], qc & 1);   // Q landed (never consumed): safe to reuse its smem
       }
       ++qc;
-      const float inv = (l > 0.f) ? 1.f / l : 0.f;
+      float inv = (l > 0.f) ? 1.f / l : 0.f;
+      if constexpr (kDrop) inv *= p.drop_rscale;
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
         uint32_t o[32];
@@ -613,10 +648,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false>
+template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false, bool kDrop = false>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk, kDrop>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -633,6 +668,7 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  if (p.drop_p8 > 0) return launch_impl<kD, kBf16, 0, false, false, true>(p, num_sms, stream);   // experimental
   if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
     switch (p.poly_every) {
       case 0: return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);

@@ -109,6 +109,12 @@ struct FwdParams {
   uint32_t sched_base;                // counter value at launch start (host-tracked: += total_work + compute CTAs)
   int dyn_sched;
   int f32x2;                          // packed fp32x2 softmax arithmetic (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
+  // attention dropout (kDrop instantiations; EXPERIMENTAL, LCA_B200_NATIVE_DROPOUT=1): keep decisions are a pure
+  // function of (seed, batch + group, global query head, global q position, global k position) -- ops/dropout.py
+  int drop_p8;                        // 0 = off; a score is dropped when its hash byte < drop_p8
+  uint32_t drop_seed;
+  float drop_rscale;                  // 256 / (256 - drop_p8)
+  int drop_head_off;                  // global index of local query head 0
 };
 
 // ---- backward -----------------------------------------------------------------------------------
@@ -157,6 +163,12 @@ struct BwdParams {
   uint32_t sched_base;
   int dyn_sched;
   int f32x2;                          // packed fp32x2 element-wise stage (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
+  // attention dropout (kDrop instantiations; EXPERIMENTAL, LCA_B200_NATIVE_DROPOUT=1): keep decisions are a pure
+  // function of (seed, batch + group, global query head, global q position, global k position) -- ops/dropout.py
+  int drop_p8;                        // 0 = off; a score is dropped when its hash byte < drop_p8
+  uint32_t drop_seed;
+  float drop_rscale;                  // 256 / (256 - drop_p8)
+  int drop_head_off;                  // global index of local query head 0
 };
 
 }  // namespace lca

@@ -301,6 +301,26 @@ __device__ __forceinline__ void ex2_poly_x2(uint64_t x, float& p0, float& p1) {
   p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
+// ---- counter-based dropout (integer recipe of lca_b200/ops/dropout.py; all arithmetic modulo 2^32) ---------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
+// everything of the key that does not depend on the key position: q position, seed, batch (+ varlen group), head
+__host__ __device__ __forceinline__ uint32_t dropout_row_key(uint32_t qpos, uint32_t seed, uint32_t batch, uint32_t head) {
+  return (qpos * 0x9E3779B1u) ^ seed ^ (((batch << 16) | head) * 0xC2B2AE3Du);
+}
+// one word decides four consecutive key positions (kpos >> 2); byte (kpos & 3) belongs to kpos
+__host__ __device__ __forceinline__ uint32_t dropout_word(uint32_t row_key, uint32_t kpos) {
+  return mix32(row_key ^ ((kpos >> 2) * 0x85EBCA77u));
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t word, uint32_t kpos, uint32_t p8) {
+  return ((word >> ((kpos & 3u) * 8u)) & 0xFFu) >= p8;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

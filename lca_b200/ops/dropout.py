@@ -5,8 +5,7 @@ Philox stream and its ring backward passes ``rng_state=None`` (``ring_flash_attn
 run can neither be reproduced on one device nor re-generate its forward masks in the backward.  Here the keep
 decision of a score is a pure function of ``(seed, batch, global head, global query position, global key position)``:
 
-    row  = mix32( qpos * 0x9E3779B1  ^  seed  ^  ((batch << 16 | head) * 0xC2B2AE3D) )
-    word = mix32( row  ^  (kpos >> 2) * 0x85EBCA77 )
+    word = mix32( qpos * 0x9E3779B1  ^  (kpos >> 2) * 0x85EBCA77  ^  seed  ^  ((batch << 16 | head) * 0xC2B2AE3D) )
     keep = byte[kpos & 3] of word  >=  p8              p8 = round(256 * dropout_p)
 
 (``mix32`` = the "lowbias32" integer finaliser; all arithmetic modulo 2**32.)  Whatever the Ulysses x Ring layout,
@@ -14,7 +13,8 @@ ring flavour or tile schedule, every rank / tile / pass regenerates the same mas
 single-device dropout bit for bit and the backward needs no saved RNG state.  The probability is quantised to
 1/256 (like flash-attn's 8-bit thresholds); ``keep_scale`` uses the quantised value, so the estimator stays unbiased.
 One 32-bit word serves four consecutive key positions: a kernel thread that owns a score row hashes once per four
-columns (the per-row part ``row`` once per tile).
+columns (8 integer instructions), and the key is a plain XOR of per-coordinate terms, so a thread that owns a KEY row
+(the dK/dV pass of the backward) pays one hash per score without any per-query pre-hash.
 
 This module is the executable specification: the PyTorch engine calls it directly, the CUDA kernels implement the
 same integer recipe (``csrc/sm100_ptx.cuh: dropout_*``).
@@ -62,7 +62,7 @@ def keep_mask(seed: int, B: int, H: int, q_pos: torch.Tensor, k_pos: torch.Tenso
         b = b + q_grp.to(torch.int64).view(1, 1, -1)
     h = torch.arange(H, device=dev, dtype=torch.int64).view(1, -1, 1) + int(head_offset)
     bh = ((b << 16) | h) & _M
-    row = _mix32(((qp * K_Q) & _M) ^ (int(seed) & _M) ^ ((bh * K_BH) & _M))            # (B,H,Sq)
+    row = ((qp * K_Q) & _M) ^ (int(seed) & _M) ^ ((bh * K_BH) & _M)                     # (B,H,Sq)
     kp = k_pos.to(torch.int64).view(1, 1, 1, -1)
     word = _mix32(row.unsqueeze(-1) ^ (((kp >> 2) * K_K) & _M))                          # (B,H,Sq,Sk)
     byte = (word >> ((kp & 3) * 8)) & 0xFF

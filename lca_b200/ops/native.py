@@ -12,6 +12,8 @@ from typing import List, Optional, Tuple
 
 import torch
 
+from . import dropout as _dropout
+
 from ..parallel.layout import PosSpec
 
 _C = None
@@ -194,9 +196,28 @@ def fmha_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p, out=None, lse=None, sm_
     for qchunk, kchunk in _chunk_by_group(qrows, krows):
         qsegs = [[r0, n, pos0, -1, r0, 0, 0, g] for (r0, n, pos0, g) in qchunk]
         ksegs = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in kchunk]
-        C.fmha_fwd(q, k, v, qsegs, ksegs, qs, ks, out, 0, lse, float(p.softmax_scale), wl, wr,
-                   float(p.softcap), alibi, 0, 0, int(sm_limit))
+        drop = _drop_args(p)
+        if drop is None:
+            C.fmha_fwd(q, k, v, qsegs, ksegs, qs, ks, out, 0, lse, float(p.softmax_scale), wl, wr,
+                       float(p.softcap), alibi, 0, 0, int(sm_limit))
+        else:
+            C.fmha_fwd_drop(q, k, v, qsegs, ksegs, qs, ks, out, 0, lse, float(p.softmax_scale), wl, wr,
+                            float(p.softcap), alibi, 0, 0, int(sm_limit), drop)
     return out, lse
+
+
+def dropout_supported(p) -> bool:
+    """EXPERIMENTAL (``LCA_B200_NATIVE_DROPOUT=1``): the ``kDrop`` kernel instantiations regenerate the coordinate-keyed
+    keep mask of ``ops/dropout.py`` in registers.  Not yet validated on hardware, hence opt-in; softcap + dropout stays
+    on the PyTorch engine."""
+    return (os.environ.get("LCA_B200_NATIVE_DROPOUT", "0") == "1" and float(getattr(p, "softcap", 0.0)) == 0.0
+            and _dropout.p8_of(p.dropout_p) > 0)
+
+
+def _drop_args(p):
+    if float(getattr(p, "dropout_p", 0.0)) <= 0.0 or _dropout.p8_of(p.dropout_p) == 0:
+        return None
+    return [_dropout.p8_of(p.dropout_p), int(p.dropout_seed) & 0xFFFFFFFF, int(p.head_offset)]
 
 
 def _chunk_by_group(qrows, krows):
@@ -275,6 +296,15 @@ def fmha_bwd(dout, q, k, v, out, lse, q_pos: PosSpec, k_pos: PosSpec, p, delta=N
     for qchunk, kchunk in _chunk_by_group(qrows, krows):
         xq = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in sorted(qchunk, key=lambda r: -r[2])]
         yk = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in kchunk]
+        drop = _drop_args(p)
+        if drop is not None:
+            C.fmha_bwd_pass_drop(False, q, dout, k, v, xq, yk, qs, ks, lse2, delta, dq, None, acc_dq,
+                                 float(p.softmax_scale), wl, wr, float(p.softcap), alibi, int(sm_limit), drop)
+            xk = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in kchunk]
+            yq = [[r0, n, pos0, -1, g] for (r0, n, pos0, g) in qchunk]
+            C.fmha_bwd_pass_drop(True, k, v, q, dout, xk, yq, ks, qs, lse2, delta, dk, dv, acc_dkv,
+                                 float(p.softmax_scale), wr, wl, float(p.softcap), alibi, int(sm_limit), drop)
+            continue
         C.fmha_bwd_pass(False, q, dout, k, v, xq, yk, qs, ks, lse2, delta, dq, None, acc_dq,
                         float(p.softmax_scale), wl, wr, float(p.softcap), alibi, int(sm_limit))
         xk = [[r0, n, pos0, g, r0] for (r0, n, pos0, g) in kchunk]

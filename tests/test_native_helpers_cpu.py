@@ -1,4 +1,7 @@
 """Host-side helpers of the native path that do not need a GPU."""
+import os
+
+import pytest
 import torch
 
 from lca_b200.ops import native
@@ -50,3 +53,45 @@ def test_block_visibility_matches_reference_step_rule():
 def test_padded_dim_and_support_messages():
     assert native._padded_dim(32) == 64 and native._padded_dim(96) == 128 and native._padded_dim(128) == 128
     assert "not on CUDA" in native.why_not(torch.zeros(1, 1, 1, 64))
+
+
+def test_dropout_hash_cxx_recipe_matches_python_spec(tmp_path):
+    """The kernels' integer dropout recipe (``csrc/sm100_ptx.cuh: mix32 / dropout_row_key / dropout_word /
+    dropout_keep``, declared ``__host__ __device__``) compiled for the HOST and compared bit for bit with
+    ``lca_b200/ops/dropout.py`` on a grid of coordinates."""
+    import shutil
+    import subprocess
+    import torch
+    from lca_b200.ops import dropout as d
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lca_b200", "ops", "csrc")
+    src = tmp_path / "h.cu"
+    src.write_text('''
+#include <cstdio>
+#include <cstdint>
+#include "sm100_ptx.cuh"
+int main() {
+  const uint32_t seed = 20240921u, p8 = 77u;
+  for (uint32_t b = 0; b < 2; ++b) for (uint32_t h = 0; h < 3; ++h)
+    for (uint32_t q = 0; q < 5; ++q) {
+      const uint32_t qpos = 1000003u * q + 17u;
+      const uint32_t rk = lca::ptx::dropout_row_key(qpos, seed, b, h + 5u);
+      for (uint32_t k = 0; k < 37; ++k) {
+        const uint32_t kpos = 262139u * (k / 9) + k;
+        std::printf("%d", lca::ptx::dropout_keep(lca::ptx::dropout_word(rk, kpos), kpos, p8) ? 1 : 0);
+      }
+      std::printf("\\n");
+    }
+  return 0;
+}
+''')
+    exe = tmp_path / "h"
+    subprocess.run([nvcc, "-std=c++17", f"-I{csrc}", "-o", str(exe), str(src)], check=True, capture_output=True)
+    lines = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    qpos = torch.tensor([1000003 * q + 17 for q in range(5)])
+    kpos = torch.tensor([262139 * (k // 9) + k for k in range(37)])
+    m = d.keep_mask(20240921, 2, 3, qpos, kpos, 77 / 256.0, head_offset=5)
+    want = ["".join(str(int(x)) for x in m[b, h, q].tolist()) for b in range(2) for h in range(3) for q in range(5)]
+    assert lines == want

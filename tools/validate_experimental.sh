@@ -40,6 +40,9 @@ step perf_dyn 120 LCA_B200_DYN_SCHED=1 S=32768 -- python tools/gpu_time_passes.p
 # 3. fp8 forward (tcgen05 kind::f8f6f4)
 step tests_fp8 300 LCA_B200_EXPERIMENTAL_FP8=1 -- python -m pytest tests/test_fp8.py -x -q -m gpu
 
+# 4. native dropout instantiations (coordinate-keyed keep mask regenerated in registers)
+step tests_dropout 300 LCA_B200_NATIVE_DROPOUT=1 -- python -m pytest tests/test_dropout_gpu.py -x -q -m gpu
+
 grep -h '"name"' "$OUT"/perf_*.log 2>/dev/null | sed 's/^/  /' > "$OUT/summary.txt"
 for f in "$OUT"/perf_*.log; do echo "$(basename "$f" .log): $(grep -h '"name"' "$f" | python -c '
 import sys, json
