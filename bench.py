@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--window", type=int, default=-1, help="sliding window (left) in tokens; -1 = none (BASELINE config 4)")
     ap.add_argument("--no-comm-probe", action="store_true",
                     help="skip the compute-only re-run that yields exposed_comm_ms (ours, N > 1; outside the timed regions)")
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                    help="cpu = control-flow dry run for the CPU test-suite (gloo, PyTorch engine, host timers); "
+                         "numbers from it are meaningless")
     ap.add_argument("--qkvpacked", action="store_true", help="LongContextAttentionQKVPacked (BASELINE config 5; MHA only)")
     return ap.parse_args()
 
@@ -87,10 +90,51 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(clocks)}
 
 
+class _HostCuda:
+    """Stand-in for the ``torch.cuda`` calls of this script in ``--device cpu`` dry runs (tests/test_bench_cpu.py)."""
+
+    class Event:
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self, stream=None):
+            import time
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return max((other.t - self.t) * 1e3, 1e-6)
+
+    class Stream:
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+    @staticmethod
+    def stream(s):
+        import contextlib
+        return contextlib.nullcontext()
+
+    @staticmethod
+    def current_stream(device=None):
+        return _HostCuda.Stream()
+
+    @staticmethod
+    def synchronize(device=None):
+        pass
+
+    @staticmethod
+    def set_device(i):
+        pass
+
+
 def main():
     a = parse()
     import torch
     import torch.distributed as dist
+    on_cpu = a.device == "cpu"
+    cu = _HostCuda if on_cpu else torch.cuda          # every CUDA runtime call below goes through `cu`
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -98,8 +142,8 @@ def main():
     if world != a.gpus:
         if world == 1 and a.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    cu.set_device(local_rank)
+    dev = torch.device("cpu") if on_cpu else torch.device("cuda", local_rank)
 
     if a.impl == "reference":
         ref_dir = os.path.join(ROOT, "baseline", "_ref")
@@ -111,7 +155,10 @@ def main():
     if need_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        if on_cpu:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+        else:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     N = world
     U = min(a.ulysses, N)
@@ -146,19 +193,27 @@ def main():
         from lca_b200.ops import native
 
         set_seq_parallel_pg(U, R, rank, world)
+        extra = {}
+        if on_cpu:                       # dry run: PyTorch engine over gloo
+            from lca_b200.kernels import AttnType
+            extra = dict(attn_type=AttnType.TORCH)
         if a.qkvpacked:
             from lca_b200 import LongContextAttentionQKVPacked
-            attn = LongContextAttentionQKVPacked(ring_impl_type=a.ring_impl, backend=a.backend)
+            attn = LongContextAttentionQKVPacked(ring_impl_type=a.ring_impl, backend=a.backend, **extra)
         else:
-            attn = LongContextAttention(ring_impl_type=a.ring_impl, backend=a.backend)
+            attn = LongContextAttention(ring_impl_type=a.ring_impl, backend=a.backend, **extra)
         launches = lambda: native.LAUNCHES
         native_ok = native.available()
-        assert native_ok, "native sm_100a extension not available on this GPU box"
+        assert native_ok or on_cpu, "native sm_100a extension not available on this GPU box"
 
     # synthetic shards, generated on host in pinned memory (this rank's S/N tokens)
     g = torch.Generator().manual_seed(1234 + rank)
-    host = [torch.randn(B, Sl, h, D, generator=g, dtype=torch.float32).to(dtype).pin_memory() for h in (H, Hkv, Hkv)]
-    host_do = torch.randn(B, Sl, H, D, generator=g, dtype=torch.float32).to(dtype).pin_memory()
+    host = [torch.randn(B, Sl, h, D, generator=g, dtype=torch.float32).to(dtype) for h in (H, Hkv, Hkv)]
+    if not on_cpu:
+        host = [t.pin_memory() for t in host]
+    host_do = torch.randn(B, Sl, H, D, generator=g, dtype=torch.float32).to(dtype)
+    if not on_cpu:
+        host_do = host_do.pin_memory()
     need_grad = a.mode == "fwdbwd"
 
     def to_dev(non_blocking=True):
@@ -170,7 +225,7 @@ def main():
         return ts
 
     dout = host_do.to(dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    flush = torch.empty((1 if on_cpu else 256) * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     kw = dict(causal=causal)
     if a.window >= 0:
@@ -192,7 +247,7 @@ def main():
     def barrier():
         if need_dist and world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        cu.synchronize()
 
     # ------------------------------------------------------------------ device-resident timing
     q, k, v = to_dev(False)[:3]
@@ -203,7 +258,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1 = cu.Event(enable_timing=True), cu.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
         step(q, k, v)
@@ -214,13 +269,13 @@ def main():
     n_launch = (launches() - l0) // max(a.steps, 1)
 
     # ------------------------------------------------------------------ end-to-end timing
-    copy_stream = torch.cuda.Stream(device=dev)
-    cur = torch.cuda.current_stream(dev)
+    copy_stream = cu.Stream(device=dev)
+    cur = cu.current_stream(dev)
 
     def prefetch():
-        with torch.cuda.stream(copy_stream):
+        with cu.stream(copy_stream):
             ts = to_dev(True)
-            ev = torch.cuda.Event()
+            ev = cu.Event()
             ev.record(copy_stream)
         return ts, ev
 
@@ -232,16 +287,17 @@ def main():
             ts, ev = nxt
             cur.wait_event(ev)
             for t in ts:
-                t.record_stream(cur)
+                if not on_cpu:
+                    t.record_stream(cur)
             if i + 1 < n:
                 nxt = prefetch()          # H2D of step i+1 overlaps the attention of step i
             out = step(*ts)
             results.append(float(out.float().mean().item()))     # D2H read of the step's result
 
     run_pipelined(3)        # warm the pipelined path with the same allocation pattern (two input sets in flight)
-    torch.cuda.synchronize(dev)
+    cu.synchronize(dev)
     barrier()
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0, t_ev1 = cu.Event(enable_timing=True), cu.Event(enable_timing=True)
     t_ev0.record()
     run_pipelined(a.steps)
     t_ev1.record()
@@ -262,10 +318,11 @@ def main():
     if a.impl == "ours" and world > 1 and not a.no_comm_probe:
         local_ms = float("nan")
         try:
-            from lca_b200.ops.attention import AttnParams
+            from lca_b200.ops.attention import AttnParams, attn_block_bwd, attn_block_fwd
             from lca_b200.parallel.layout import Seg, ring_positions
             Sr, Hl, Hkvl = U * Sl, H // U, max(Hkv // U, 1)
-            gq = torch.Generator(device=dev).manual_seed(99 + rank)
+            gq = torch.Generator(device=dev)
+            gq.manual_seed(99 + rank)
             qb = torch.randn(B, Sr, Hl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
             dob = torch.randn(B, Sr, Hl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
             kf = torch.randn(B, S, Hkvl, D, generator=gq, device=dev, dtype=torch.float32).to(dtype)
@@ -276,21 +333,21 @@ def main():
             k_pos = (Seg(0, S, 1),)
 
             def local_step():
-                o, l = native.fmha_fwd(qb, kf, vf, q_pos, k_pos, pp)
+                o, l = attn_block_fwd(qb, kf, vf, q_pos, k_pos, pp)        # native tcgen05 kernels on a GPU box
                 if need_grad:
-                    native.fmha_bwd(dob, qb, kf, vf, o, l, q_pos, k_pos, pp)
+                    attn_block_bwd(dob, qb, kf, vf, o, l, q_pos, k_pos, pp)
 
             for _ in range(2):
                 local_step()
-            torch.cuda.synchronize(dev)
+            cu.synchronize(dev)
             n_probe = max(1, min(a.steps, 5))
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0, c1 = cu.Event(enable_timing=True), cu.Event(enable_timing=True)
             c0.record()
             for _ in range(n_probe):
                 local_step()
                 flush.fill_(1)
             c1.record()
-            torch.cuda.synchronize(dev)
+            cu.synchronize(dev)
             local_ms = c0.elapsed_time(c1) / n_probe
             del qb, dob, kf, vf
         except Exception as e:  # noqa: BLE001 - the probe must never cost the headline number
