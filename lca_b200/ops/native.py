@@ -35,7 +35,8 @@ def _load():
 
 LAUNCHES = 0     # number of in-tree CUDA kernels launched through this module (bench.py reports it)
 _KERNEL_FUNCS = {"fmha_fwd", "fmha_bwd_pass", "merge_out_lse", "finalize_out", "flatten_varlen_lse",
-                 "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd_pass", "symm_wait"}
+                 "unflatten_varlen_lse", "permute_group", "attn_delta", "usp_fwd", "usp_bwd_pass", "symm_wait",
+                 "fmha_fwd_drop", "fmha_bwd_pass_drop", "fmha_fwd_fp8", "quantize_e4m3"}
 
 
 class _CountingExt:
