@@ -467,6 +467,10 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   TORCH_CHECK(lse2.size(0) == B && lse2.size(1) == Hq, "lse2 shape");
   std::memset(&p, 0, sizeof(p));
   p.f32x2 = f32x2_enabled();
+  {
+    static int sp = [] { const char* v = std::getenv("LCA_B200_BWD_SPLIT"); return (v && std::atoi(v) == 1) ? 1 : 0; }();
+    p.split = sp;
+  }
   make_tmap(&p.tm_x0, x0, "x0", 128);
   make_tmap(&p.tm_x1, x1, "x1", 128);
   make_tmap(&p.tm_y0, y0, "y0", 64);

@@ -176,7 +176,13 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 }  // namespace
 
 // kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop>
+// kSplit (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1): BOTH element-wise warpgroups work on EVERY streamed tile, each on one
+//   32-column half (default: warpgroup wg owns the tiles with j % 2 == wg).  The per-tile critical path
+//   T GEMMs -> element-wise -> accumulate GEMMs gets half as long, which is what bounds the tensor pipe today
+//   (2 stages: utilisation ~ 2*T_mma / (T_mma + T_elementwise)).  The packed 16-bit P / dS of half h is written at
+//   columns [32h, 32h+16) of its stage, i.e. inside the fp32 columns its own warpgroup has already consumed, so the
+//   two warpgroups never touch each other's columns and need no extra barrier; the MMA issuer reads A from there.
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
@@ -245,13 +251,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     mbar_init(acc_empty, 8);
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full + 8 * s, 1);
-      mbar_init(p_full + 8 * s, 4);
+      mbar_init(p_full + 8 * s, kSplit ? 8 : 4);
     }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(y_full + 8 * s, 1);
       mbar_init(y_empty + 8 * s, 1);
       mbar_init(st_full + 8 * s, 32);
-      mbar_init(st_empty + 8 * s, 4);
+      mbar_init(st_empty + 8 * s, kSplit ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -354,12 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BY / 16; ++kk)   // acc0 += dS * Y0
-            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + kk * 8,
+            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + (kSplit ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8),
                    make_sw128_desc(y0 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
           if constexpr (kIsDKV) {
 #pragma unroll
             for (int kk = 0; kk < BY / 16; ++kk)   // acc1 += P * Y1
-              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + kk * 8,
+              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + (kSplit ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8),
                      make_sw128_desc(y1 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
           }
         };
@@ -426,9 +432,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tT0 = tmem + lane_base + C::TMEM_T0 + wg * BY;
-    const uint32_t tT1 = tmem + lane_base + C::TMEM_T1 + wg * BY;
+    const uint32_t tT0_wg = tmem + lane_base + C::TMEM_T0 + wg * BY;
+    const uint32_t tT1_wg = tmem + lane_base + C::TMEM_T1 + wg * BY;
     uint32_t tc = 0, yc = 0, afc = 0, xcw = 0;
+    uint32_t tcs[2] = {0, 0};          // kSplit: per-stage t_full phase counters (both warpgroups see every tile)
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -454,11 +461,22 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         const uint32_t st = yc % C::STAGES;
         const uint32_t ypar = (yc / C::STAGES) & 1;
         ++yc;
-        if ((j & 1) != wg) { ++j; continue; }
+        if constexpr (!kSplit) {
+          if ((j & 1) != wg) { ++j; continue; }
+        }
+        const int sT = kSplit ? (j & 1) : wg;                     // TMEM stage of this tile
+        const uint32_t tT0 = kSplit ? tmem + lane_base + C::TMEM_T0 + sT * BY : tT0_wg;
+        const uint32_t tT1 = kSplit ? tmem + lane_base + C::TMEM_T1 + sT * BY : tT1_wg;
+        const int h_begin = kSplit ? wg : 0, h_end = kSplit ? wg + 1 : 2;   // 32-column halves this warpgroup handles
         const int hq = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx;     // query head (ALiBi slope index)
         const float slope = p.alibi ? p.alibi[wk.b * p.alibi_bstride + hq] : 0.f;
-        mbar_wait(t_full + 8 * wg, tc & 1);
-        ++tc;
+        if constexpr (kSplit) {
+          mbar_wait(t_full + 8 * sT, tcs[sT] & 1);
+          ++tcs[sT];
+        } else {
+          mbar_wait(t_full + 8 * wg, tc & 1);
+          ++tc;
+        }
         if constexpr (kIsDKV) mbar_wait(st_full + 8 * st, ypar);
         tc_fence_after();
         const int yb = it.ypos0 + (it.nvalid - 1) * p.y_pos_stride;
@@ -471,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           // general pre-pass (rolled, keeps the hot loop small): rewrite T0 as masked log2-domain logits
           // and T1 as dl + (T1 - dl) * softcap'(s), so the common loop below needs no special cases.
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          for (int half = h_begin; half < h_end; ++half) {
             uint32_t t0[32], t1[32];
             tmem_ld32(tT0 + half * 32, t0);
             tmem_ld32(tT1 + half * 32, t1);
@@ -500,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           mul = 1.f;
         }
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = h_begin; half < h_end; ++half) {
           uint32_t t0[32], t1[32];
           tmem_ld32(tT0 + half * 32, t0);
           tmem_ld32(tT1 + half * 32, t1);
@@ -573,14 +591,14 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             ds[(c >> 1)] = pack2<kBf16>(dv[0], dv[1]);
             ds[(c >> 1) + 1] = pack2<kBf16>(dv[2], dv[3]);
           }
-          if constexpr (kIsDKV) tmem_st16(tT0 + half * 16, pp);
-          tmem_st16(tT1 + half * 16, ds);
+          if constexpr (kIsDKV) tmem_st16(tT0 + half * (kSplit ? 32 : 16), pp);
+          tmem_st16(tT1 + half * (kSplit ? 32 : 16), ds);
         }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(p_full + 8 * wg);
+          mbar_arrive(p_full + 8 * sT);
           if constexpr (kIsDKV) mbar_arrive(st_empty + 8 * st);
         }
         ++j;
@@ -645,10 +663,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false, bool kSplit = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -668,6 +686,13 @@ static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cud
   if (p.drop_p8 > 0)                  // experimental dropout variant (static schedule, scalar arithmetic)
     return is_dkv ? launch_impl<kD, kBf16, true, false, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, false, true>(p, num_sms, stream);
+  if (p.split && !p.dyn_sched) {      // experimental: both warpgroups on every streamed tile (static schedule only)
+    if (p.f32x2)
+      return is_dkv ? launch_impl<kD, kBf16, true, false, true, false, true>(p, num_sms, stream)
+                    : launch_impl<kD, kBf16, false, false, true, false, true>(p, num_sms, stream);
+    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, true>(p, num_sms, stream)
+                  : launch_impl<kD, kBf16, false, false, false, false, true>(p, num_sms, stream);
+  }
   if (p.f32x2 && !p.dyn_sched)        // experimental packed element-wise stage (static schedule only)
     return is_dkv ? launch_impl<kD, kBf16, true, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, true>(p, num_sms, stream);

@@ -169,6 +169,7 @@ struct BwdParams {
   uint32_t drop_seed;
   float drop_rscale;                  // 256 / (256 - drop_p8)
   int drop_head_off;                  // global index of local query head 0
+  int split;                          // kSplit instantiations (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1)
 };
 
 }  // namespace lca

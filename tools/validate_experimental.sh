@@ -33,6 +33,12 @@ for pe in 3 4; do
   step perf_f32x2_poly$pe 120 LCA_B200_F32X2=1 LCA_B200_POLY_EVERY=$pe S=32768 -- python tools/gpu_time_passes.py
 done
 
+# 1b. backward with both element-wise warpgroups on every streamed tile (halves the per-tile critical path)
+step tests_split 420 LCA_B200_BWD_SPLIT=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "bwd or backward or padded or module"
+step perf_split 120 LCA_B200_BWD_SPLIT=1 S=32768 -- python tools/gpu_time_passes.py
+step tests_split_f32x2 420 LCA_B200_BWD_SPLIT=1 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "bwd or backward or padded or module"
+step perf_split_f32x2 120 LCA_B200_BWD_SPLIT=1 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
+
 # 2. dynamic tile scheduler
 step tests_dyn 420 LCA_B200_DYN_SCHED=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
 step perf_dyn 120 LCA_B200_DYN_SCHED=1 S=32768 -- python tools/gpu_time_passes.py
