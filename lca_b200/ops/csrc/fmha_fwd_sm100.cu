@@ -672,6 +672,7 @@ static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t str
   if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
     switch (p.poly_every) {
       case 0: return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);
+      case 2: return launch_impl<kD, kBf16, 2, false, true>(p, num_sms, stream);   // half of the pairs: D=64 is MUFU-bound 2:1
       case 3: return launch_impl<kD, kBf16, 3, false, true>(p, num_sms, stream);
       case 4: return launch_impl<kD, kBf16, 4, false, true>(p, num_sms, stream);
       default: return launch_impl<kD, kBf16, 6, false, true>(p, num_sms, stream);

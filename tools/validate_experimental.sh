@@ -29,9 +29,13 @@ step perf_default 120 S=32768 -- python tools/gpu_time_passes.py
 # 1. packed fp32x2 softmax / dS arithmetic (FFMA2 / FADD2 / FMUL2)
 step tests_f32x2 420 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
 step perf_f32x2 120 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
-for pe in 3 4; do
+for pe in 2 3 4; do
   step perf_f32x2_poly$pe 120 LCA_B200_F32X2=1 LCA_B200_POLY_EVERY=$pe S=32768 -- python tools/gpu_time_passes.py
 done
+for pe in 2 3 6; do          # head_dim 64: exponentials outnumber the tensor work 2:1, needs the heaviest offload
+  step perf_d64_f32x2_poly$pe 120 LCA_B200_F32X2=1 LCA_B200_POLY_EVERY=$pe S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
+done
+step perf_d64_default 120 S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
 
 # 1b. backward with both element-wise warpgroups on every streamed tile (halves the per-tile critical path)
 step tests_split 420 LCA_B200_BWD_SPLIT=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "bwd or backward or padded or module"
