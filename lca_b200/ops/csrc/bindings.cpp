@@ -103,7 +103,8 @@ static int num_sms() {
 }
 
 // ---- dynamic tile scheduler state (EXPERIMENTAL, LCA_B200_DYN_SCHED=1): one monotonic counter per device; the host
-// tracks its value at the start of each launch (every launch claims total_work + #compute-CTA indices).  Assumes the
+// tracks its value at the start of each launch (every launch claims total_work + #CTAs indices: each CTA, push CTAs
+// included, makes exactly one failing claim).  Assumes the
 // launches of one device are issued in stream order (single compute stream).
 struct SchedState {
   at::Tensor counter;
@@ -132,7 +133,8 @@ static void attach_sched(P& p, const at::Tensor& like, int sms, int n_comm) {
   const int avail = sms - n_comm;
   int gc = p.total_work < avail ? p.total_work : avail;
   if (gc < 1) gc = 1;
-  st.base += static_cast<uint32_t>(p.total_work) + static_cast<uint32_t>(gc);
+  // every claiming CTA makes exactly one failing claim; the push CTAs claim too once their transfers are out
+  st.base += static_cast<uint32_t>(p.total_work) + static_cast<uint32_t>(gc) + static_cast<uint32_t>(n_comm);
 }
 
 #define LCA_CUDA_OK(expr)                                                                   \
