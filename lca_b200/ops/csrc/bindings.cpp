@@ -291,8 +291,11 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
                       int64_t Hkv) {
   TORCH_CHECK(mesh.size() == 7, "mesh arity");
   const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
-  TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
+  // peer_slabs may carry one extra trailing entry: the NVLS multicast address of the slab (EXPERIMENTAL broadcast push)
+  const bool has_mc = static_cast<int>(peer_slabs.size()) == P + 1;
+  TORCH_CHECK(P == U * R && P <= kMaxPeers && (static_cast<int>(peer_slabs.size()) == P || has_mc) &&
               static_cast<int>(peer_sigs.size()) == P, "peer tables");
+  TORCH_CHECK(!has_mc || P < kMaxPeers, "the multicast address travels in the last peer slot");
   c.n_comm = static_cast<int>(mesh[6]);
   TORCH_CHECK(c.n_comm >= 1 && c.n_comm <= 64, "n_comm");
   c.P = P; c.U = U; c.R = R;
@@ -333,6 +336,7 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
     c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
     c.peer_sig[i] = reinterpret_cast<unsigned int*>(peer_sigs[i]);
   }
+  if (has_mc && peer_slabs[P] != 0) c.peer_slab[kMaxPeers - 1] = reinterpret_cast<unsigned char*>(peer_slabs[P]);
   c.my_sig = reinterpret_cast<unsigned int*>(my_sig);
   c.stage_q_rows = stage_q_rows; c.stage_kv_rows = stage_kv_rows;
   c.epoch = static_cast<unsigned int>(epoch);

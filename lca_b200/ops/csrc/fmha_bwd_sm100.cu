@@ -182,11 +182,11 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 //   (2 stages: utilisation ~ 2*T_mma / (T_mma + T_elementwise)).  The packed 16-bit P / dS of half h is written at
 //   columns [32h, 32h+16) of its stage, i.e. inside the fp32 columns its own warpgroup has already consumed, so the
 //   two warpgroups never touch each other's columns and need no extra barrier; the MMA issuer reads A from there.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit, bool kMc>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
-    comm_cta(p.comm);
+    comm_cta<kMc>(p.comm);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
     // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
@@ -665,10 +665,11 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false, bool kSplit = false>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false, bool kSplit = false,
+          bool kMc = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit, kMc>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -685,6 +686,9 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
+  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental NVLS broadcast push
+    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
+                  : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
   if (p.drop_p8 > 0)                  // experimental dropout variant (static schedule, scalar arithmetic)
     return is_dkv ? launch_impl<kD, kBf16, true, false, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, false, true>(p, num_sms, stream);

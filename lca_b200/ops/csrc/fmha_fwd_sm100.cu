@@ -147,14 +147,15 @@ struct Bars {
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
 // kDyn: work items are claimed from a global atomic counter by the producer warp and broadcast to the other roles
 // kDrop: attention dropout regenerated from global coordinates (sm100_ptx.cuh: dropout_*; experimental, opt-in)
+// kMc: the push CTAs broadcast K/V through the slab's NVLS multicast address (usp_comm.cuh; experimental, opt-in)
 // kPk: the unmasked softmax runs on packed fp32x2 instructions (FFMA2 / FADD2): scale-and-subtract, the polynomial
 //      exp2 and the row sum issue once per element pair (experimental, opt-in: LCA_B200_F32X2=1)
 //       through a 2-deep smem ring (EXPERIMENTAL); otherwise the static snake schedule is used.
-template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk, bool kDrop>
+template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk, bool kDrop, bool kMc>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
-    comm_cta(p.comm);
+    comm_cta<kMc>(p.comm);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
     // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
@@ -650,10 +651,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false, bool kDrop = false>
+template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false, bool kDrop = false, bool kMc = false>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk, kDrop>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk, kDrop, kMc>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -670,6 +671,8 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental NVLS broadcast push
+    return launch_impl<kD, kBf16, 6, false, false, false, true>(p, num_sms, stream);
   if (p.drop_p8 > 0) return launch_impl<kD, kBf16, 0, false, false, true>(p, num_sms, stream);   // experimental
   if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
     switch (p.poly_every) {

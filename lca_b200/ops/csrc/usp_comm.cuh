@@ -60,6 +60,41 @@ __device__ __forceinline__ void comm_copy(const CopyMsg& m, int B, int tid, int 
   }
 }
 
+// Same loop with system-scope strong stores: the destination is an NVLS *multicast* address (one store is replicated
+// by the NVSwitch into every rank's slab); multimem addresses must be written with multimem.st.
+__device__ __forceinline__ void comm_copy_mc(const CopyMsg& m, int B, int tid, int nthreads) {
+  const long long total = static_cast<long long>(B) * m.nrows * m.row_vecs;
+  constexpr int UNR = 4;
+  for (long long base = static_cast<long long>(tid) * UNR; base < total; base += static_cast<long long>(nthreads) * UNR) {
+    uint4 val[UNR];
+    long long doff[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; ++j) {
+      const long long i = base + j;
+      doff[j] = -1;
+      if (i < total) {
+        const int c = static_cast<int>(i % m.row_vecs);
+        const long long br = i / m.row_vecs;
+        const int row = static_cast<int>(br % m.nrows);
+        const int b = static_cast<int>(br / m.nrows);
+        val[j] = *reinterpret_cast<const uint4*>(m.src + b * m.src_sb + row * m.src_ss + c * 16);
+        doff[j] = b * m.dst_sb + row * m.dst_ss + c * 16;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; ++j)
+      if (doff[j] >= 0)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m.dst + doff[j]),
+                     "f"(__uint_as_float(val[j].x)), "f"(__uint_as_float(val[j].y)), "f"(__uint_as_float(val[j].z)),
+                     "f"(__uint_as_float(val[j].w))
+                     : "memory");
+  }
+}
+
+// kMc (EXPERIMENTAL, LCA_B200_NVLS=1 with the VMM slab): when the host put the slab's NVLS multicast address into
+// peer_slab[kMaxPeers - 1], everything that goes to EVERY rank (K/V; in the owner-computes backward also Q, dO and the
+// row statistics) is written ONCE to the multicast window instead of P times to unicast peers: NVLink egress / P.
+template <bool kMc>
 static __device__ __noinline__ void comm_cta(const CommParams& c) {
   using namespace ptx;
   const int tid = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -70,9 +105,63 @@ static __device__ __noinline__ void comm_cta(const CommParams& c) {
     st_release_sys(c.peer_sig[threadIdx.x] + kSigRTR + me, c.epoch);
   const long long row_off_kv = (static_cast<long long>(c.r) * c.U + c.u) * c.rows;
   const long long row_off_q = static_cast<long long>(c.u) * c.rows;
+  bool mc = false;
+  if constexpr (kMc) {
+    unsigned char* mcb = c.peer_slab[kMaxPeers - 1];
+    // a head slice per destination exists only when heads are scattered (U > 1); the broadcast needs ONE slice for all
+    mc = (mcb != nullptr) && (c.U == 1);
+    if (mc) {
+      if (static_cast<int>(threadIdx.x) < c.P) spin_until_ge(c.my_sig + kSigRTR + threadIdx.x, c.epoch, 32);
+      __syncthreads();                    // every rank has entered this call: all staging buffers may be overwritten
+      CopyMsg m;
+      m.nrows = c.rows;
+      m.row_vecs = c.Hkvl * c.D * esz / 16;
+      m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
+      m.dst_sb = c.stage_kv_rows * m.dst_ss;
+      for (int t = 0; t < c.n_kv; ++t) {
+        m.src = static_cast<const unsigned char*>(c.kvt[t].src);
+        m.src_sb = c.kvt[t].sb * esz; m.src_ss = c.kvt[t].ss * esz;
+        m.dst = mcb + c.kvt[t].off + row_off_kv * m.dst_ss;
+        comm_copy_mc(m, c.B, tid, nthreads);
+      }
+      if (c.q_to_all) {
+        m.row_vecs = c.Hl * c.D * esz / 16;
+        m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
+        m.dst_sb = c.stage_kv_rows * m.dst_ss;
+        for (int t = 0; t < c.n_q; ++t) {
+          m.src = static_cast<const unsigned char*>(c.qt[t].src);
+          m.src_sb = c.qt[t].sb * esz; m.src_ss = c.qt[t].ss * esz;
+          m.dst = mcb + c.qt[t].off + row_off_kv * m.dst_ss;
+          comm_copy_mc(m, c.B, tid, nthreads);
+        }
+        for (int t = 0; t < c.n_stat; ++t) {
+          CopyMsg s;
+          s.nrows = c.Hl;
+          s.row_vecs = c.rows * 4 / 16;
+          s.src = reinterpret_cast<const unsigned char*>(c.stat[t]);
+          s.src_sb = static_cast<long long>(c.H) * c.rows * 4;
+          s.src_ss = static_cast<long long>(c.rows) * 4;
+          s.dst = mcb + c.stat_off[t] + row_off_kv * 4;
+          s.dst_sb = static_cast<long long>(c.Hl) * c.stage_kv_rows * 4;
+          s.dst_ss = c.stage_kv_rows * 4;
+          comm_copy_mc(s, c.B, tid, nthreads);
+        }
+      }
+      __threadfence_system();
+      __syncthreads();
+    }
+  }
   for (int i = 0; i < c.P; ++i) {
     const int d = (me + i) % c.P;
     const int du = d % c.U, dr = d / c.U;
+    if (mc) {                             // payload already broadcast: only the arrival counters remain
+      if (threadIdx.x == 0) {
+        red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
+        if (dr == c.r) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
+        red_add_release_sys(c.peer_sig[d] + kSigQA + me, 1u);
+      }
+      continue;
+    }
     if (threadIdx.x == 0) {
       spin_until_ge(c.my_sig + kSigRTR + d, c.epoch, 32);
     }

@@ -150,6 +150,15 @@ class FusedUSPEngine:
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
         self.sig = _make_slab(SIG_BYTES, sp_group, device)
 
+    def _push_ptrs(self, slab):
+        """Peer slab addresses for a launch that carries push CTAs.  EXPERIMENTAL (``LCA_B200_NVLS=1`` together with
+        ``LCA_B200_SLAB=vmm``): on a pure ring (U == 1) the slab's NVLS multicast address rides along as one extra
+        entry and the push CTAs broadcast K/V (backward: also Q, dO, statistics) with ONE store instead of P."""
+        mc = getattr(slab, "multicast_ptr", 0)
+        if mc and self.U == 1 and self.P < 16 and os.environ.get("LCA_B200_NVLS", "0") == "1":
+            return list(slab.peer_ptrs) + [mc]
+        return slab.peer_ptrs
+
     def supports_shapes(self, q, k) -> bool:
         """Shapes the push CTAs / kernels can handle; anything else takes the collective path."""
         rows, H, Hkv = q.shape[1], q.shape[2], k.shape[2]
@@ -231,7 +240,7 @@ class FusedUSPEngine:
                   float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
                   [P, U, R, u, r, rows, self.n_comm],
                   [self.off_q, self.off_k, self.off_v, Sr, P * rows],
-                  slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
+                  self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
         if push_q:   # the symmetric buffers are reused by the next call
             out = out_local.clone()
             lse_own = slab.tensor(self.off_lse_own, (B, H, rows), torch.float32).clone()
@@ -351,7 +360,7 @@ class FusedUSPEngine:
                        u * Hl, float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe,
                        [P, U, R, u, r, rows, self.n_comm], [q, dout], [self.off_q, self.off_do], [k, v],
                        [self.off_k, self.off_v], [delta_local, lse2_local], [self.off_delta, self.off_lse2], True, Sr, S,
-                       slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
+                       self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
         # ---- pass 2: dK/dV of my ring block's keys (stationary) against EVERY rank's queries (streamed)
         xk = [[row0, n, pos0, 0, row0 - src * rows, SIG_KV + src, slab.peer_ptrs[src] + self.off_dk,
                slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0) in mine]
@@ -413,7 +422,7 @@ class FusedUSPEngine:
         C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,
                        float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe, mesh, ql, qo, [k, v],
                        [self.off_k, self.off_v], [delta_local] if pushed else [], [self.off_delta] if pushed else [],
-                       False, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
+                       False, Sr, P * rows, self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
         # ---- pass 2: dK/dV for every K/V row I hold, reduced into the owners' accumulators
         h0 = u * Hkvl if Hkv >= U else (u * Hkv) // U
         xk, n_my_kv_tiles = [], 0

@@ -6,7 +6,8 @@
 #
 # 1. fused test-suite for this GPU count (default build)                      -> tests_default.log
 # 2. the same with the opt-in kernel variants that passed tools/validate_experimental.sh (pass them as FLAGS=...)
-# 3. LCA_B200_SLAB=vmm (torch symmetric memory / CUDA VMM slab): tests, then the combination that hung once in
+# 3. LCA_B200_SLAB=vmm (torch symmetric memory / CUDA VMM slab): tests, NVLS broadcast push on top of it
+#    (LCA_B200_NVLS=1, pure-ring meshes), then the combination that hung once in
 #    round 1 (fused forward + NCCL backward) under a short timeout
 # 4. bench.py fwd+bwd and fwd at N GPUs, both arms, with the exposed-communication probe
 # Everything lands in gpurun_out/multigpu_n$N/.  Every step has its own timeout.
@@ -38,6 +39,8 @@ if [ -n "$FLAGS" ]; then
   step tests_flags 420 $FLAGS -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 fi
 step tests_vmm 420 LCA_B200_SLAB=vmm -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
+step tests_nvls 420 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
+step bench_ours_fb_nvls 300 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- $TR --master-port 29617 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
 step hang_repro_ipc 150 LCA_B200_FUSED_BWD=0 -- $TR --master-port 29611 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --no-comm-probe
 step hang_repro_vmm 150 LCA_B200_FUSED_BWD=0 LCA_B200_SLAB=vmm -- $TR --master-port 29612 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --no-comm-probe
 step bench_ref_fb 400 -- $TR --master-port 29613 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --impl reference
