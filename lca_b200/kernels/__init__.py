@@ -73,6 +73,12 @@ def is_torch_type(t) -> bool:
 
 def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_processor: torch.nn.Module = None):
     """Return a callable for ``stage`` in {"fwd-only", "bwd-only", "fwd-bwd"} (``kernels/__init__.py:63-65``)."""
+    if not isinstance(impl_type, AttnType):
+        # the reference's last resort (``kernels/__init__.py:292-295``): an unknown implementation tag with a
+        # user-supplied attention module returns that module
+        if attn_processor is not None:
+            return attn_processor
+        raise ValueError(f"Unknown flash attention implementation: {impl_type}")
     if impl_type in _FOREIGN:
         raise ValueError(f"AttnType.{impl_type.name} targets {_FOREIGN[impl_type]}; not available in the B200 build")
     if stage not in ("fwd-only", "bwd-only", "fwd-bwd"):
