@@ -39,6 +39,11 @@ if [ -n "$FLAGS" ]; then
   step tests_flags 420 $FLAGS -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 fi
 step tests_vmm 420 LCA_B200_SLAB=vmm -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
+step tests_fastpush 420 LCA_B200_FAST_PUSH=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
+step bench_ours_fb_fastpush 300 LCA_B200_FAST_PUSH=1 -- $TR --master-port 29618 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
+step bench_ours_fwd_fastpush_2cta 300 LCA_B200_FAST_PUSH=1 LCA_B200_COMM_CTAS=2 -- $TR --master-port 29619 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ" --mode fwd
+step bench_ulysses_default 300 -- $TR --master-port 29620 bench.py --gpus "$N" --steps 10 --warmup 3 --seq 32768 --heads 32 --ulysses "$N" --ring-impl basic --mode fwd
+step bench_ulysses_fastpush 300 LCA_B200_FAST_PUSH=1 -- $TR --master-port 29621 bench.py --gpus "$N" --steps 10 --warmup 3 --seq 32768 --heads 32 --ulysses "$N" --ring-impl basic --mode fwd
 step tests_nvls 420 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 step bench_ours_fb_nvls 300 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- $TR --master-port 29617 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
 step hang_repro_ipc 150 LCA_B200_FUSED_BWD=0 -- $TR --master-port 29611 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --no-comm-probe
