@@ -426,13 +426,34 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           mul = 1.f;
         }
         uint32_t v[128];
+        if constexpr (kPk) {
+          if (!general) {
+            // the row max of the first 64 columns overlaps the TMEM load of the last 64 (tcgen05.wait::ld is all-or-nothing)
+            tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_wait_ld();
+            tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
+            tmem_ld32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
-        tmem_wait_ld();
-        if (!general) {
+            for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-          mx *= p.scale_log2;
+            for (int c = 64; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            mx *= p.scale_log2;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+            tmem_wait_ld();
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+          tmem_wait_ld();
+          if (!general) {
+#pragma unroll
+            for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            mx *= p.scale_log2;
+          }
         }
         // ---- running max with lazy rescale
         const float m_new = fmaxf(m, mx);
@@ -537,6 +558,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
             if (c & 2) acc_b = ptx::add_f32x2(acc_b, ptx::pack_f32x2(p0, p1));
             else acc_a = ptx::add_f32x2(acc_a, ptx::pack_f32x2(p0, p1));
             v[c >> 1] = pack2<kBf16>(p0, p1);
+            // columns 0-63 are final: their 32 packed words go back to TMEM while the second half is computed
+            if (c == 62) tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           }
           float s0, s1;
           ptx::unpack_f32x2(ptx::add_f32x2(acc_a, acc_b), s0, s1);
@@ -560,8 +583,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           }
         }
         l += rs;
-        tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tmem_st32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        if constexpr (kPk && !kDrop) {
+          if (general) tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));   // unmasked tiles stored it mid-loop
+          tmem_st32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        } else {
+          tmem_st32(tS, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_st32(tS + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
