@@ -247,6 +247,20 @@ static void set_dropout(P& p, const std::vector<int64_t>& drop, double softcap) 
   p.drop_head_off = static_cast<int>(drop[2]);
 }
 
+// The fused launches (usp_fwd / usp_bwd_pass) have long positional signatures; dropout for the NEXT fused launch of
+// this thread is handed over separately (EXPERIMENTAL, consumed by exactly one launch).
+static thread_local std::vector<int64_t> g_next_drop;
+void set_next_dropout(const std::vector<int64_t>& drop) { g_next_drop = drop; }
+template <typename P>
+static void take_next_dropout(P& p, double softcap) {
+  if (g_next_drop.empty()) return;
+  std::vector<int64_t> d;
+  d.swap(g_next_drop);
+  set_dropout(p, d, softcap);
+  TORCH_CHECK(p.comm.n_comm == 0 || p.comm.peer_slab[kMaxPeers - 1] == nullptr,
+              "native dropout cannot be combined with the experimental push engine / NVLS broadcast yet");
+}
+
 static void fmha_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                           const std::vector<std::vector<int64_t>>& qsegs, const std::vector<std::vector<int64_t>>& ksegs,
                           int64_t q_pos_stride, int64_t k_pos_stride, at::Tensor& out, int64_t o_head_off, at::Tensor& lse,
@@ -446,7 +460,8 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
   if (mesh.at(1) > 1) { ql.push_back(uq); qo.push_back(offs[0]); }
   fill_comm(p.comm, mesh, ql, qo, kvl, kvo, {}, {}, false, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
             o_target, uq.size(2), uk.size(2));
-  attach_sched(p, q, num_sms(), p.comm.n_comm);
+  take_next_dropout(p, softcap);
+  if (p.drop_p8 == 0) attach_sched(p, q, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }
@@ -616,7 +631,8 @@ void usp_bwd_pass(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const
   if (!mesh.empty())
     fill_comm(p.comm, mesh, qlike, q_offs, kvlike, kv_offs, stats, stat_offs, q_to_all, stage_q_rows, stage_kv_rows,
               peer_slabs, peer_sigs, my_sig, epoch, o_target, H, Hkv);
-  attach_sched(p, x0, num_sms(), p.comm.n_comm);
+  take_next_dropout(p, softcap);
+  if (p.drop_p8 == 0) attach_sched(p, x0, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_bwd(p, static_cast<int>(x0.size(3)), x0.scalar_type() == at::kBFloat16, is_dkv, num_sms(),
                               at::cuda::getCurrentCUDAStream()));
 }
@@ -735,6 +751,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
+  m.def("set_next_dropout", &lca::set_next_dropout, "EXPERIMENTAL: {p8, seed, head_offset} for the next fused launch");
   m.def("fmha_fwd_drop", &lca::fmha_fwd_drop, "EXPERIMENTAL: forward with coordinate-keyed dropout");
   m.def("fmha_bwd_pass_drop", &lca::fmha_bwd_pass_drop, "EXPERIMENTAL: backward pass with coordinate-keyed dropout");
   m.def("merge_out_lse", &lca::merge_out_lse, "in-place online-softmax merge");

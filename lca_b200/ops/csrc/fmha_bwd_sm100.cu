@@ -686,12 +686,12 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
-  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental NVLS broadcast push
-    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
-                  : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
   if (p.drop_p8 > 0)                  // experimental dropout variant (static schedule, scalar arithmetic)
     return is_dkv ? launch_impl<kD, kBf16, true, false, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, false, true>(p, num_sms, stream);
+  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
+    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
+                  : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
   if (p.split && !p.dyn_sched) {      // experimental: both warpgroups on every streamed tile (static schedule only)
     if (p.f32x2)
       return is_dkv ? launch_impl<kD, kBf16, true, false, true, false, true>(p, num_sms, stream)

@@ -699,9 +699,9 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
-  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental NVLS broadcast push
-    return launch_impl<kD, kBf16, 6, false, false, false, true>(p, num_sms, stream);
   if (p.drop_p8 > 0) return launch_impl<kD, kBf16, 0, false, false, true>(p, num_sms, stream);   // experimental
+  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
+    return launch_impl<kD, kBf16, 6, false, false, false, true>(p, num_sms, stream);
   if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
     switch (p.poly_every) {
       case 0: return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);

@@ -240,6 +240,7 @@ class FusedUSPEngine:
             o_target = self.o_total & 0xFFFFFFFF
         else:
             o_target = 0
+        self._arm_dropout(p, Hl)
         C.usp_fwd(qst, kst, vst, q, k, v, qsegs, ksegs, qstride, qstride, out_local, u * Hl, lse,
                   float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
                   [P, U, R, u, r, rows, self.n_comm],
@@ -360,6 +361,7 @@ class FusedUSPEngine:
         xq = [[row0, n, pos0, 0, row0 - src * rows, SIG_QA + src, slab.peer_ptrs[src] + self.off_o, 0,
                self.sig.peer_ptrs[src] + 4 * SIG_ODONE] for (src, row0, n, pos0) in sorted(mine, key=lambda t: -t[3])]
         self.o_total += U * B * Hl * tiles_of_me * 2
+        self._arm_dropout(p, Hl)
         C.usp_bwd_pass(False, q_all, do_all, kst, vst, xq, ksegs, stride, stride, lse2_all, delta_all, dq_own, None, 0,
                        u * Hl, float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe,
                        [P, U, R, u, r, rows, self.n_comm], [q, dout], [self.off_q, self.off_do], [k, v],
@@ -370,6 +372,7 @@ class FusedUSPEngine:
                slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0) in mine]
         yq = [[row0, n, pos0, SIG_QA + src, 0] for (src, row0, n, pos0) in all_segs]
         self.dkv_total += U * B * Hkvl * tiles_of_me * 2
+        self._arm_dropout(p, Hl)
         C.usp_bwd_pass(True, kst, vst, q_all, do_all, xk, yq, stride, stride, lse2_all, delta_all, dk_own, dv_own, 0,
                        u * Hkvl, float(p.softmax_scale), wr, wl, float(p.softcap), alibi, self.sig.ptr, fe, [], [], [], [],
                        [], [], [], False, Sr, S, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
@@ -423,6 +426,7 @@ class FusedUSPEngine:
             o_target = 0
         mesh = [P, U, R, u, r, rows, self.n_comm]
         ql, qo = ([q, dout], [self.off_q, self.off_do]) if pushed else ([], [])
+        self._arm_dropout(p, Hl)
         C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,
                        float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe, mesh, ql, qo, [k, v],
                        [self.off_k, self.off_v], [delta_local] if pushed else [], [self.off_delta] if pushed else [],
@@ -439,6 +443,7 @@ class FusedUSPEngine:
                 n_my_kv_tiles += (s[1] + 127) // 128
         yq = [[s[0], s[1], s[2], s[3], s[7]] for s in qsegs]
         self.dkv_total += P * B * Hkvl * n_my_kv_tiles * 2
+        self._arm_dropout(p, Hl)
         C.usp_bwd_pass(True, kst, vst, qst, dost, xk, yq, stride, stride, lse2, delta_c, dk_acc, dv_acc, 3, h0,
                        float(p.softmax_scale), wr, wl, float(p.softcap), alibi, self.sig.ptr, fe, [], [], [], [], [],
                        [], [], False, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, 0, H, Hkv)
@@ -447,9 +452,20 @@ class FusedUSPEngine:
         return dq, dk_acc.to(k.dtype), dv_acc.to(v.dtype)
 
     # ------------------------------------------------------------------------------ autograd entry
-    def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic):
-        p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, 0.0, deterministic)
+    def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
+                  dropout_p: float = 0.0, dropout_seed: int = 0):
+        p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
+        if p.dropout_p > 0.0:        # EXPERIMENTAL (native.dropout_supported): the mask needs no communication at all
+            from dataclasses import replace
+            p = replace(p, dropout_seed=int(dropout_seed))
         return _FusedAttnFunc.apply(q, k, v, self, canonical_variant(variant), p)
+
+    def _arm_dropout(self, p: AttnParams, Hl: int) -> None:
+        """Hand the dropout key to the NEXT fused launch: local query head h of this rank is global head u*Hl + h."""
+        if p.dropout_p > 0.0:
+            from ..ops import dropout as _d
+            native.ext().set_next_dropout([_d.p8_of(p.dropout_p), int(p.dropout_seed) & 0xFFFFFFFF,
+                                           self.u * Hl + int(p.head_offset)])
 
 
 def _dense_heads(t: torch.Tensor) -> torch.Tensor:
@@ -503,7 +519,7 @@ class _FusedAttnFunc(torch.autograd.Function):
             hl = q.shape[2] // eng.U
             alibi = alibi[..., eng.u * hl:(eng.u + 1) * hl].contiguous()
         from dataclasses import replace
-        pl = replace(p, alibi_slopes=alibi)
+        pl = replace(p, alibi_slopes=alibi, head_offset=eng.u * (q.shape[2] // eng.U) if eng.U > 1 else p.head_offset)
         if eng.R == 1:      # no ring dimension: `None` would mean the WORLD group to the ring loop
             rg = _SelfGroup
         dq, dk, dv = ring_attn_backward(rg, a2a(dout), a2a(q), a2a(k), a2a(v), a2a(out), lse, ctx.variant, pl)

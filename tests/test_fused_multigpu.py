@@ -136,3 +136,39 @@ def test_fused_batch2_2gpu(U, R, variant):
         pytest.skip("needs 2 GPUs")
     run_distributed(_worker, 2, U, R, variant, dict(causal=True, _b1=False), 4, 2, 1024, 128, "hybrid", True,
                     backend="nccl", timeout=90)
+
+
+def _dropout_worker(rank, world, U, R, variant):
+    """Fused USP kernels with native dropout == single-device dropout with the same seed (coordinate-keyed masks)."""
+    from lca_b200 import EXTRACT_FUNC_DICT, LongContextAttention, set_seq_parallel_pg
+    from lca_b200.kernels.attention import pytorch_attn_func
+    dev = torch.device("cuda", rank)
+    B, S, H, Hkv, D = 1, 1024, 4, 2, 128
+    g = torch.Generator().manual_seed(5)
+    q, k, v, do = (torch.randn(B, S, h, D, generator=g).to(dev, torch.bfloat16) for h in (H, Hkv, Hkv, H))
+    kw = dict(causal=True, dropout_p=0.2)
+    q1, k1, v1 = (t.clone().requires_grad_() for t in (q, k, v))
+    torch.manual_seed(777)                               # the dropout seed is drawn from torch's CPU generator
+    ref = pytorch_attn_func(q1, k1, v1, **kw)
+    ref.backward(do)
+    set_seq_parallel_pg(U, R, rank, world)
+    key = {"basic": "basic", "zigzag": "zigzag", "stripe": "strip"}[variant]
+    sh = lambda t: EXTRACT_FUNC_DICT[key](t, rank, world, rd=R, ud=U).detach().clone()
+    lq, lk, lv = (sh(t).requires_grad_() for t in (q, k, v))
+    attn = LongContextAttention(ring_impl_type=key, backend="fused")
+    torch.manual_seed(777)
+    out = attn(lq, lk, lv, **kw)
+    torch.testing.assert_close(out.float(), sh(ref.detach()).float(), atol=3e-2, rtol=0)
+    out.backward(sh(do))
+    for a, b, n in ((lq.grad, q1.grad, "dq"), (lk.grad, k1.grad, "dk"), (lv.grad, v1.grad, "dv")):
+        ref_g = sh(b).float()
+        err = (a.float() - ref_g).abs().max().item()
+        assert err / (ref_g.abs().max().item() + 1e-6) < 4e-2, f"{n}: {err}"
+    torch.cuda.synchronize()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
+@pytest.mark.skipif(os.environ.get("LCA_B200_NATIVE_DROPOUT", "0") != "1", reason="native dropout kernels are opt-in")
+@pytest.mark.parametrize("U,R,variant", [(1, 2, "zigzag"), (2, 1, "basic")])
+def test_fused_dropout_2gpu(U, R, variant):
+    run_distributed(_dropout_worker, 2, U, R, variant, backend="nccl")

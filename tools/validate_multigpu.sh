@@ -38,6 +38,7 @@ if [ -n "$FLAGS" ]; then
   # shellcheck disable=SC2086
   step tests_flags 420 $FLAGS -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 fi
+step tests_fused_dropout 300 LCA_B200_NATIVE_DROPOUT=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "dropout"
 step tests_vmm 420 LCA_B200_SLAB=vmm -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 step tests_fastpush 420 LCA_B200_FAST_PUSH=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 step bench_ours_fb_fastpush 300 LCA_B200_FAST_PUSH=1 -- $TR --master-port 29618 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
