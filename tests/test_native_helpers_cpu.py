@@ -95,3 +95,24 @@ int main() {
     m = d.keep_mask(20240921, 2, 3, qpos, kpos, 77 / 256.0, head_offset=5)
     want = ["".join(str(int(x)) for x in m[b, h, q].tolist()) for b in range(2) for h in range(3) for q in range(5)]
     assert lines == want
+
+
+def test_exp2_polynomial_accuracy_claim():
+    """``ex2_poly`` (FMA-pipe exp2 of the forward softmax, ``csrc/sm100_ptx.cuh``): the coefficients are read from the
+    header and the recipe is replayed in float32 -- max relative error must stay at the documented 1.0e-4, far below
+    the bf16 rounding (3.9e-3) applied to P right after."""
+    import re
+    import numpy as np
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lca_b200", "ops", "csrc",
+                            "sm100_ptx.cuh")).read()
+    body = src[src.index("float ex2_poly(float x)"):]
+    c3, c2, c1 = (np.float32(v) for v in re.search(
+        r"fmaf\(fmaf\(fmaf\(([0-9.]+)f, f, ([0-9.]+)f\), f, ([0-9.]+)f\), f, 1\.0f\)", body).groups())
+    magic = np.float32(12582912.0)
+    x = np.linspace(-40, 0, 1_000_001, dtype=np.float32)
+    t = (np.maximum(x, np.float32(-126)) + magic).astype(np.float32)
+    f = (x - (t - magic).astype(np.float32)).astype(np.float32)
+    p = ((((c3 * f + c2).astype(np.float32) * f + c1).astype(np.float32)) * f + np.float32(1)).astype(np.float32)
+    y = (p.view(np.int32) + (t.view(np.int32) << 23)).view(np.float32).astype(np.float64)
+    ref = np.exp2(x.astype(np.float64))
+    assert float(np.max(np.abs(y - ref) / ref)) < 1.1e-4
