@@ -2,7 +2,7 @@
 # Second GPU call of a round (N GPUs, default 2): multi-GPU validation of what cannot be checked on one GPU.
 #
 #   gpurun --gpus 2 --timeout 1500 -- 'bash tools/validate_multigpu.sh 2'
-#   gpurun --gpus 8 --timeout 1500 -- 'bash tools/validate_multigpu.sh 8'
+#   gpurun --gpus 8 --timeout 900 -- 'QUICK=1 FLAGS="..." bash tools/validate_multigpu.sh 8'     (charged 8x: keep it short)
 #
 # 1. fused test-suite for this GPU count (default build)                      -> tests_default.log
 # 2. the same with the opt-in kernel variants that passed tools/validate_experimental.sh (pass them as FLAGS=...)
@@ -38,6 +38,7 @@ if [ -n "$FLAGS" ]; then
   # shellcheck disable=SC2086
   step tests_flags 420 $FLAGS -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 fi
+if [ "${QUICK:-0}" != "1" ]; then     # QUICK=1 (use it at 8 GPUs: charged 8x): default tests + the bench arms only
 step tests_fused_dropout 300 LCA_B200_NATIVE_DROPOUT=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "dropout"
 step tests_vmm 420 LCA_B200_SLAB=vmm -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
 step tests_fastpush 420 LCA_B200_FAST_PUSH=1 -- python -m pytest tests/test_fused_multigpu.py -x -q -k "${N}gpu"
@@ -49,6 +50,7 @@ step tests_nvls 420 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- python -m pytest tests/
 step bench_ours_fb_nvls 300 LCA_B200_SLAB=vmm LCA_B200_NVLS=1 -- $TR --master-port 29617 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
 step hang_repro_ipc 150 LCA_B200_FUSED_BWD=0 -- $TR --master-port 29611 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --no-comm-probe
 step hang_repro_vmm 150 LCA_B200_FUSED_BWD=0 LCA_B200_SLAB=vmm -- $TR --master-port 29612 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --no-comm-probe
+fi
 step bench_ref_fb 400 -- $TR --master-port 29613 bench.py --gpus "$N" --steps 3 --warmup 3 --seq "$SEQ" --impl reference
 step bench_ours_fb 300 -- $TR --master-port 29614 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ"
 step bench_ours_fwd 300 -- $TR --master-port 29615 bench.py --gpus "$N" --steps 5 --warmup 3 --seq "$SEQ" --mode fwd
