@@ -1,0 +1,88 @@
+"""Property-based tests (hypothesis) of the pure-Python algebra everything else rests on: layouts, position segments,
+the block-visibility test that lets ring steps be skipped, and the dropout key."""
+import torch
+from hypothesis import given, settings, strategies as st
+
+from lca_b200.ops.attention import AttnParams, block_is_visible
+from lca_b200.ops.ref_attention import _bias_and_mask
+from lca_b200.parallel.layout import (EXTRACT_FUNC_DICT, Seg, gather_global, local_token_index, pos_tensor,
+                                      ring_positions, slice_pos, varlen_positions)
+
+VARIANTS = ["basic", "zigzag", "stripe"]
+mesh = st.sampled_from([(1, 1), (1, 2), (2, 1), (2, 2), (1, 4), (4, 1), (2, 4), (4, 2), (1, 8), (8, 1)])
+
+
+@settings(max_examples=60, deadline=None)
+@given(mesh, st.sampled_from(VARIANTS), st.integers(1, 6), st.integers(1, 3))
+def test_extract_then_gather_is_identity(UR, variant, chunk, H):
+    U, R = UR
+    P = U * R
+    S = 2 * P * chunk                                   # zigzag needs 2P | S
+    x = torch.arange(S * H, dtype=torch.float32).view(1, S, H, 1)
+    key = "strip" if variant == "stripe" else variant
+    shards = [EXTRACT_FUNC_DICT[key](x, rank, P, rd=R, ud=U) for rank in range(P)]
+    assert torch.equal(gather_global(variant, shards, R, U), x)
+    idx = torch.cat([local_token_index(variant, S, rank % U, rank // U, U, R) for rank in range(P)])
+    assert sorted(idx.tolist()) == list(range(S))       # a partition of the tokens
+    for rank in range(P):                               # the shard really is x[index map]
+        assert torch.equal(shards[rank], x[:, local_token_index(variant, S, rank % U, rank // U, U, R)])
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.sampled_from(VARIANTS), st.integers(1, 8), st.integers(1, 5), st.data())
+def test_ring_positions_and_slicing(variant, R, chunk, data):
+    L = 2 * chunk                                       # local tokens per ring rank
+    allpos = []
+    for r in range(R):
+        spec = ring_positions(variant, r, R, L)
+        pos = pos_tensor(spec, "cpu")
+        assert pos.numel() == L
+        allpos += pos.tolist()
+        a = data.draw(st.integers(0, L))
+        b = data.draw(st.integers(a, L))
+        assert torch.equal(pos_tensor(slice_pos(spec, a, b), "cpu"), pos[a:b]) if b > a else True
+    assert sorted(allpos) == list(range(R * L))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.sampled_from(["basic", "zigzag"]), st.integers(1, 4), st.lists(st.integers(1, 4), min_size=1, max_size=4))
+def test_varlen_positions_cover_every_sequence_once(variant, R, chunks):
+    lens = [2 * R * c for c in chunks]                  # global lengths, evenly divisible as the reference requires
+    local = [l // R for l in lens]
+    cu = [0]
+    for l in local:
+        cu.append(cu[-1] + l)
+    seen = {i: [] for i in range(len(lens))}
+    for r in range(R):
+        for s in varlen_positions(variant, r, R, cu):
+            seen[s.group] += [s.start + i * s.stride for i in range(s.count)]
+    for i, l in enumerate(lens):
+        assert sorted(seen[i]) == list(range(l))
+
+
+segs = st.lists(st.tuples(st.integers(0, 60), st.integers(1, 12), st.sampled_from([1, 2, 4]), st.integers(0, 1)),
+                min_size=1, max_size=3).map(lambda xs: tuple(Seg(a, n, s, g) for a, n, s, g in xs))
+
+
+@settings(max_examples=200, deadline=None)
+@given(segs, segs, st.booleans(), st.integers(-1, 20), st.integers(-1, 20))
+def test_block_visibility_never_skips_a_visible_pair(q_pos, k_pos, causal, wl, wr):
+    """Soundness of the ring-step skip: ``block_is_visible == False`` must imply that the exact mask hides every pair
+    (the converse may be conservative)."""
+    p = AttnParams(1.0, causal, (wl, wr))
+    from lca_b200.parallel.layout import group_tensor
+    mask, _ = _bias_and_mask(pos_tensor(q_pos, "cpu"), pos_tensor(k_pos, "cpu"), causal, (wl, wr), None, 1, "cpu",
+                             group_tensor(q_pos, "cpu"), group_tensor(k_pos, "cpu"))
+    any_visible = True if mask is None else bool((~mask).any())
+    if not block_is_visible(q_pos, k_pos, p):
+        assert not any_visible
+
+
+@settings(max_examples=50, deadline=None)
+@given(st.integers(0, 2**31 - 1), st.integers(0, 3), st.integers(0, 7), st.integers(0, 2**20), st.integers(0, 2**20))
+def test_dropout_key_is_a_function_of_global_coordinates(seed, b, h, q0, k0):
+    from lca_b200.ops import dropout as d
+    qp, kp = torch.arange(q0, q0 + 5), torch.arange(k0, k0 + 9)
+    full = d.keep_mask(seed, b + 1, h + 1, qp, kp, 0.37)
+    one = d.keep_mask(seed, 1, 1, qp[2:4], kp[3:8], 0.37, head_offset=h, batch_offset=b)
+    assert torch.equal(one[0, 0], full[b, h, 2:4, 3:8])
