@@ -86,3 +86,26 @@ def test_dropout_key_is_a_function_of_global_coordinates(seed, b, h, q0, k0):
     full = d.keep_mask(seed, b + 1, h + 1, qp, kp, 0.37)
     one = d.keep_mask(seed, 1, 1, qp[2:4], kp[3:8], 0.37, head_offset=h, batch_offset=b)
     assert torch.equal(one[0, 0], full[b, h, 2:4, 3:8])
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.integers(1, 3), min_size=1, max_size=40))
+def test_chunk_by_group_keeps_groups_whole_and_within_the_segment_budget(segs_per_group):
+    """Many-sequence varlen batches are launched in chunks of whole attention groups with <= MAX_SEG segments per side
+    (``native._chunk_by_group``): every segment appears exactly once, a group is never split across launches."""
+    from lca_b200.ops.native import MAX_SEG, _chunk_by_group
+    qrows, krows, row = [], [], 0
+    for g, n in enumerate(segs_per_group):
+        for _ in range(n):
+            qrows.append((row, 4, 0, g))
+            krows.append((row, 4, 0, g))
+            row += 4
+    seen_q, seen_k, group_launch = [], [], {}
+    for li, (qc, kc) in enumerate(_chunk_by_group(qrows, krows)):
+        assert 0 < len(qc) <= MAX_SEG and 0 < len(kc) <= MAX_SEG
+        assert {r[3] for r in qc} == {r[3] for r in kc}
+        for r in qc:
+            assert group_launch.setdefault(r[3], li) == li
+        seen_q += qc
+        seen_k += kc
+    assert sorted(seen_q) == sorted(qrows) and sorted(seen_k) == sorted(krows)
