@@ -109,3 +109,53 @@ def test_chunk_by_group_keeps_groups_whole_and_within_the_segment_budget(segs_pe
         seen_q += qc
         seen_k += kc
     assert sorted(seen_q) == sorted(qrows) and sorted(seen_k) == sorted(krows)
+
+
+def _tile_iter_twin(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN):
+    """Python transcription of the kernels' ``TileIter::next`` (``csrc/fmha_fwd_sm100.cu``; the backward's iterator is
+    the same with X/Y renamed): K/V tiles a block of query rows visits, tiles fully outside the window skipped."""
+    qmin, qmax = q_pos0, q_pos0 + (q_rows - 1) * q_stride
+    visited = []
+    for si, (row0, nrows, pos0, group) in enumerate(ksegs):
+        nt = (nrows + BN - 1) // BN if group == q_group else 0
+        for kt in range(nt):
+            r0 = kt * BN
+            nv = min(BN, nrows - r0)
+            ka = pos0 + r0 * k_stride
+            kb = ka + (nv - 1) * k_stride
+            if wr >= 0 and ka - qmax > wr:
+                break                                   # later tiles of this segment are further right
+            if wl >= 0 and qmin - kb > wl:
+                continue                                # entirely left of the window
+            visited.append((si, kt))
+    return visited
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(0, 300), st.integers(1, 24), st.sampled_from([1, 2, 4]), st.integers(0, 1),
+       st.lists(st.tuples(st.integers(1, 40), st.integers(0, 300), st.integers(0, 1)), min_size=1, max_size=4),
+       st.sampled_from([1, 2, 4]), st.integers(-1, 64), st.integers(-1, 64), st.booleans())
+def test_tile_skipping_never_drops_a_visible_tile(q_pos0, q_rows, q_stride, q_group, kdefs, k_stride, wl, wr, causal):
+    BN = 8
+    if causal:
+        wr = 0                                          # native.window_bounds: causal => right bound 0
+    ksegs, row = [], 0
+    for nrows, pos0, group in kdefs:
+        ksegs.append((row, nrows, pos0, group))
+        row += nrows
+    visited = set(_tile_iter_twin(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN))
+    qpos = q_pos0 + q_stride * torch.arange(q_rows)
+    for si, (row0, nrows, pos0, group) in enumerate(ksegs):
+        for kt in range((nrows + BN - 1) // BN):
+            nv = min(BN, nrows - kt * BN)
+            kpos = pos0 + k_stride * (kt * BN + torch.arange(nv))
+            rel = kpos.view(1, -1) - qpos.view(-1, 1)
+            vis = torch.ones_like(rel, dtype=torch.bool)
+            if wr >= 0:
+                vis &= rel <= wr
+            if wl >= 0:
+                vis &= rel >= -wl
+            if group != q_group:
+                vis &= False
+            if bool(vis.any()):
+                assert (si, kt) in visited, (si, kt)
