@@ -115,6 +115,11 @@ static int f32x2_enabled() {
   static int e = [] { const char* v = std::getenv("LCA_B200_F32X2"); return (v && std::atoi(v) == 1) ? 1 : 0; }();
   return e;
 }
+// forward with 64-row K/V tiles and double-buffered scores (EXPERIMENTAL, LCA_B200_FWD_BN64=1)
+static bool bn64_enabled() {
+  static bool e = [] { const char* v = std::getenv("LCA_B200_FWD_BN64"); return v && std::atoi(v) == 1; }();
+  return e;
+}
 static bool dyn_sched_enabled() {
   static bool e = [] { const char* v = std::getenv("LCA_B200_DYN_SCHED"); return v && std::atoi(v) == 1; }();
   return e;
@@ -273,6 +278,13 @@ static void fmha_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Te
   set_dropout(p, drop, softcap);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
+  if (bn64_enabled() && p.drop_p8 == 0) {
+    make_tmap(&p.tm_k, k, "k", 64);
+    make_tmap(&p.tm_v, v, "v", 64);
+    LCA_CUDA_OK(launch_fmha_fwd_bn64(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
+                                     at::cuda::getCurrentCUDAStream()));
+    return;
+  }
   if (p.drop_p8 == 0) attach_sched(p, q, sms, 0);     // the dropout instantiations use the static schedule
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
                               at::cuda::getCurrentCUDAStream()));
@@ -461,6 +473,13 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
   fill_comm(p.comm, mesh, ql, qo, kvl, kvo, {}, {}, false, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
             o_target, uq.size(2), uk.size(2));
   take_next_dropout(p, softcap);
+  if (bn64_enabled() && p.drop_p8 == 0 && p.comm.peer_slab[kMaxPeers - 1] == nullptr) {
+    make_tmap(&p.tm_k, k, "k", 64);
+    make_tmap(&p.tm_v, v, "v", 64);
+    LCA_CUDA_OK(launch_fmha_fwd_bn64(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
+                                     at::cuda::getCurrentCUDAStream()));
+    return;
+  }
   if (p.drop_p8 == 0) attach_sched(p, q, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 out=profiles/sass_summary.txt
 : > $out
-for o in lca_b200/ops/build/fmha_fwd_sm100.o lca_b200/ops/build/fmha_bwd_sm100.o lca_b200/ops/build/fmha_fwd_fp8_sm100.o; do
+for o in lca_b200/ops/build/fmha_fwd_sm100.o lca_b200/ops/build/fmha_bwd_sm100.o lca_b200/ops/build/fmha_fwd_fp8_sm100.o lca_b200/ops/build/fmha_fwd_bn64_sm100.o; do
   for fn in $(cuobjdump -sass $o | grep -oE "Function : [^ ]+" | awk '{print $3}' | sort -u); do
     body=$(cuobjdump -sass -fun "$fn" $o)
     echo "== $(echo $fn | c++filt)" >> $out

@@ -37,6 +37,12 @@ for pe in 2 3 6; do          # head_dim 64: exponentials outnumber the tensor wo
 done
 step perf_d64_default 120 S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
 
+# 1a. forward with 64-row K/V tiles and double-buffered scores (separate kernel file, scalar softmax arithmetic)
+step tests_bn64 420 LCA_B200_FWD_BN64=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "fwd or module or padded or varlen or util"
+step perf_bn64 120 LCA_B200_FWD_BN64=1 S=32768 -- python tools/gpu_time_passes.py
+step perf_bn64_poly3 120 LCA_B200_FWD_BN64=1 LCA_B200_POLY_EVERY=3 S=32768 -- python tools/gpu_time_passes.py
+step perf_bn64_d64 120 LCA_B200_FWD_BN64=1 LCA_B200_POLY_EVERY=3 S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
+
 # 1b. backward with both element-wise warpgroups on every streamed tile (halves the per-tile critical path)
 step tests_split 420 LCA_B200_BWD_SPLIT=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "bwd or backward or padded or module"
 step perf_split 120 LCA_B200_BWD_SPLIT=1 S=32768 -- python tools/gpu_time_passes.py
