@@ -268,7 +268,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid
           mbar_wait(q_full + 8 * t, qc[t] & 1);
           ++qc[t];
         }
-        if (!more) continue;
+        if (!more) {
+          // empty work item (no visible K/V tile): still hand the Q tiles back through o_full, so the warpgroups can
+          // only release q_empty AFTER this warp has passed its q_full wait (a one-bit phase parity must never be
+          // allowed to advance twice under a waiter)
+          for (int t = 0; t < nt; ++t) mma_commit(o_full + 8 * t);
+          continue;
+        }
         const uint32_t base = kvc;
         int n_qk = 0;                               // score tiles issued so far
         // prologue: fill both score stages
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS0 = tmem + lane_base + C::TMEM_S + t * 128;
     const uint32_t tO = tmem + lane_base + C::TMEM_O + t * kD;
-    uint32_t scbits = 0, oc = 0, qc = 0;     // s_full phase parity of this tile, bit = stage
+    uint32_t scbits = 0, oc = 0;             // s_full phase parity of this tile, bit = stage
     uint32_t pvc = 0;                    // PV MMAs of this Q tile committed before the current work item
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
@@ -452,14 +458,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid
       pvc += static_cast<uint32_t>(j);
       // ---- epilogue: O / l -> 16-bit -> smem (XOR-swizzled 16B chunks) -> coalesced global stores
       uint8_t* stage = smem_gen + C::OFF_Q + t * C::QTILE_BYTES;
-      if (j > 0) {
-        mbar_wait(o_full + 8 * t, oc & 1);
-        ++oc;
-        tc_fence_after();
-      } else {
-        mbar_wait(q_full + 8 * t, qc & 1);   // Q landed (never consumed): safe to reuse its smem
-      }
-      ++qc;
+      mbar_wait(o_full + 8 * t, oc & 1);     // committed by the MMA warp for every work item, empty ones included
+      ++oc;
+      tc_fence_after();
       const float inv = (l > 0.f) ? 1.f / l : 0.f;
 #pragma unroll
       for (int c = 0; c < kD / 32; ++c) {
