@@ -488,6 +488,73 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
 // ------------------------------------------------------------------------------------ fmha bwd
 // One pass of the backward (see fmha_bwd_sm100.cu).  x0/x1 stationary, y0/y1 streamed.
 // xsegs[i] = {row0, nrows, pos0, group, o_row0 [, flag, o_base0, o_base1, o_sig]};  ysegs[i] = {row0, nrows, pos0, flag, group}
+// True when some 128-row stationary tile of the launch has NO visible streamed tile under the kernel's own skipping
+// rule (TileIter in fmha_bwd_sm100.cu: a streamed 64-row tile [ka, kb] of the same group is visited unless
+// ka - xmax > wr or xmin - kb > wl).  ka and kb grow with the tile index, so per (stationary tile, streamed segment) the
+// visible tiles are an index interval [lo, hi]: O(1).  Such launches take the kXfix instantiation of the dQ pass.
+static bool has_empty_stationary_tile(const BwdParams& p) {
+  constexpr int64_t BXr = 128, BYr = 64;
+  for (int xi = 0; xi < p.n_xseg; ++xi) {
+    const XSegD& xs = p.xseg[xi];
+    const int64_t ntx = (xs.nrows + BXr - 1) / BXr;
+    for (int64_t t = 0; t < ntx; ++t) {
+      const int64_t rows = std::min<int64_t>(BXr, xs.nrows - t * BXr);
+      const int64_t xmin = xs.pos0 + t * BXr * p.x_pos_stride;
+      const int64_t xmax = xmin + (rows - 1) * p.x_pos_stride;
+      bool visible = false;
+      for (int yi = 0; yi < p.n_yseg && !visible; ++yi) {
+        const KSegD& ys = p.yseg[yi];
+        if (ys.group != xs.group || ys.nrows <= 0) continue;
+        const int64_t nt = (ys.nrows + BYr - 1) / BYr;
+        const int64_t step = BYr * p.y_pos_stride;               // position step between tile starts (> 0)
+        int64_t lo = 0, hi = nt - 1;
+        if (p.wr >= 0) {                                         // ka(k) = pos0 + k*step <= xmax + wr
+          const int64_t lim = xmax + p.wr - ys.pos0;
+          if (lim < 0) continue;
+          hi = std::min<int64_t>(hi, lim / step);
+        }
+        if (p.wl >= 0) {                                         // kb(k) >= xmin - wl
+          const int64_t need = xmin - p.wl;
+          const int64_t kb_last = ys.pos0 + static_cast<int64_t>(ys.nrows - 1) * p.y_pos_stride;
+          if (kb_last < need) continue;
+          // full tiles: kb(k) = pos0 + k*step + (BYr-1)*stride
+          const int64_t num = need - ys.pos0 - (BYr - 1) * p.y_pos_stride;
+          int64_t k = num <= 0 ? 0 : (num + step - 1) / step;
+          lo = std::min<int64_t>(k, nt - 1);                     // the (possibly partial) last tile reaches kb_last >= need
+        }
+        visible = lo <= hi;
+      }
+      if (!visible) return true;
+    }
+  }
+  return false;
+}
+
+// host-only entry for the CPU test-suite: xsegs[i] = {nrows, pos0, group}, ysegs[i] = {nrows, pos0, group}
+bool debug_has_empty_tile(const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+                          int64_t x_pos_stride, int64_t y_pos_stride, int64_t wl, int64_t wr) {
+  BwdParams p;
+  std::memset(&p, 0, sizeof(p));
+  TORCH_CHECK(xsegs.size() <= kMaxSeg && ysegs.size() <= kMaxSeg, "segment count");
+  p.n_xseg = static_cast<int>(xsegs.size());
+  p.n_yseg = static_cast<int>(ysegs.size());
+  for (int i = 0; i < p.n_xseg; ++i) {
+    p.xseg[i].nrows = static_cast<int>(xsegs[i].at(0));
+    p.xseg[i].pos0 = static_cast<int>(xsegs[i].at(1));
+    p.xseg[i].group = static_cast<int>(xsegs[i].at(2));
+  }
+  for (int i = 0; i < p.n_yseg; ++i) {
+    p.yseg[i].nrows = static_cast<int>(ysegs[i].at(0));
+    p.yseg[i].pos0 = static_cast<int>(ysegs[i].at(1));
+    p.yseg[i].group = static_cast<int>(ysegs[i].at(2));
+  }
+  p.x_pos_stride = static_cast<int>(x_pos_stride);
+  p.y_pos_stride = static_cast<int>(y_pos_stride);
+  p.wl = static_cast<int>(wl);
+  p.wr = static_cast<int>(wr);
+  return has_empty_stationary_tile(p);
+}
+
 static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
                    const at::Tensor& y1, const std::vector<std::vector<int64_t>>& xsegs,
                    const std::vector<std::vector<int64_t>>& ysegs, int64_t x_pos_stride, int64_t y_pos_stride,
@@ -580,6 +647,7 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
     TORCH_CHECK(reinterpret_cast<uintptr_t>(p.out1) % 16 == 0, "out1 alignment");
   }
   p.out_mode = static_cast<int>(out_mode);
+  if (!is_dkv) p.xfix = has_empty_stationary_tile(p) ? 1 : 0;
 }
 
 static void fmha_bwd_pass_impl(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
@@ -770,6 +838,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
+  m.def("debug_has_empty_tile", &lca::debug_has_empty_tile, "host-only: does a dQ-pass launch contain an empty work item?");
   m.def("set_next_dropout", &lca::set_next_dropout, "EXPERIMENTAL: {p8, seed, head_offset} for the next fused launch");
   m.def("fmha_fwd_drop", &lca::fmha_fwd_drop, "EXPERIMENTAL: forward with coordinate-keyed dropout");
   m.def("fmha_bwd_pass_drop", &lca::fmha_bwd_pass_drop, "EXPERIMENTAL: backward pass with coordinate-keyed dropout");

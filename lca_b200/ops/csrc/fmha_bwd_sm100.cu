@@ -176,13 +176,22 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 }  // namespace
 
 // kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
+// kXfix: dQ pass only.  The element-wise warps wait x_full once per work item (their lse2/delta reads must be ordered
+//   after a peer's push), but x_empty is released by the MMA warp alone.  For a work item WITHOUT any visible streamed
+//   tile the MMA warp releases it at once, the producer reloads X, and x_full can complete two phases while a
+//   warpgroup is still in the previous item's epilogue: its one-bit parity wait then blocks forever (found by the
+//   protocol model tests/test_bwd_pipeline_model_cpu.py; matches the one hang seen in round 1: collective zigzag
+//   backward, where early-chunk Q tiles see no key of a later rank's block).  With kXfix every element-wise warp also
+//   arrives on x_empty (count 9) right after its x_full wait, so X cannot be reloaded under a waiter.  The host
+//   selects this instantiation exactly for the launches that contain such empty work items (bindings.cpp), which
+//   leaves the hardware-validated instruction streams in place everywhere else.
 // kSplit (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1): BOTH element-wise warpgroups work on EVERY streamed tile, each on one
 //   32-column half (default: warpgroup wg owns the tiles with j % 2 == wg).  The per-tile critical path
 //   T GEMMs -> element-wise -> accumulate GEMMs gets half as long, which is what bounds the tensor pipe today
 //   (2 stages: utilisation ~ 2*T_mma / (T_mma + T_elementwise)).  The packed 16-bit P / dS of half h is written at
 //   columns [32h, 32h+16) of its stage, i.e. inside the fp32 columns its own warpgroup has already consumed, so the
 //   two warpgroups never touch each other's columns and need no extra barrier; the MMA issuer reads A from there.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit, bool kMc>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit, bool kMc, bool kXfix>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       }
     }
     mbar_init(x_full, 1);
-    mbar_init(x_empty, 1);
+    mbar_init(x_empty, (kXfix && !kIsDKV) ? 9 : 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 8);
     for (int s = 0; s < 2; ++s) {
@@ -451,6 +460,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         // acquired the arrival flag before issuing the tile's TMA, so x_full orders our reads after the push
         mbar_wait(x_full, xcw & 1);
         ++xcw;
+        if constexpr (kXfix) {
+          if (lane == 0) mbar_arrive(x_empty);     // this warp has consumed the phase: X may be reloaded
+        }
         if (row_ok) {
           lse2_r = p.lse2[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
           delta_r = p.delta[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
@@ -666,10 +678,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------
 template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false, bool kSplit = false,
-          bool kMc = false>
+          bool kMc = false, bool kXfix = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit, kMc>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit, kMc, kXfix>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -692,6 +704,8 @@ static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cud
   if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
     return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
+  if (p.xfix && !is_dkv)              // dQ pass with work items that see no streamed tile (see kXfix above)
+    return launch_impl<kD, kBf16, false, false, false, false, false, false, true>(p, num_sms, stream);
   if (p.split && !p.dyn_sched) {      // experimental: both warpgroups on every streamed tile (static schedule only)
     if (p.f32x2)
       return is_dkv ? launch_impl<kD, kBf16, true, false, true, false, true>(p, num_sms, stream)

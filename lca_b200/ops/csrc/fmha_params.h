@@ -170,6 +170,7 @@ struct BwdParams {
   float drop_rscale;                  // 256 / (256 - drop_p8)
   int drop_head_off;                  // global index of local query head 0
   int split;                          // kSplit instantiations (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1)
+  int xfix;                           // dQ pass: some stationary tile sees no streamed tile -> kXfix instantiation
 };
 
 }  // namespace lca

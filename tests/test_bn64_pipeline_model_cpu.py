@@ -31,10 +31,12 @@ class MBar:
                 self.phase += 1
                 self.cv.notify_all()
 
-    def wait(self, parity, timeout=20.0):
+    TIMEOUT = 20.0
+
+    def wait(self, parity, timeout=None):
         """mbarrier.try_wait.parity: returns once the phase with this parity has completed."""
         with self.cv:
-            ok = self.cv.wait_for(lambda: (self.phase & 1) != parity, timeout)
+            ok = self.cv.wait_for(lambda: (self.phase & 1) != parity, timeout or MBar.TIMEOUT)
             assert ok, "deadlock: barrier wait timed out"
 
 
