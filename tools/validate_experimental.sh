@@ -26,6 +26,16 @@ step() {   # step <name> <timeout_s> <env...> -- <cmd...>
 # 0. reference point: default build
 step perf_default 120 S=32768 -- python tools/gpu_time_passes.py
 
+# 0b. the round-1 hang and its fix (dQ pass, empty work items): the fixed kernel must finish and match the oracle;
+#     the pre-fix kernel is EXPECTED to hang sooner or later (timeout 40 s; reported, not counted as a failure)
+step xfix_fixed 180 -- python tools/gpu_repro_xfix.py
+echo "=== xfix_prefix_repro (LCA_B200_NO_XFIX=1; a timeout here CONFIRMS the diagnosis)"
+if LCA_B200_NO_XFIX=1 timeout 40 python tools/gpu_repro_xfix.py --no-check > "$OUT/xfix_prefix_repro.log" 2>&1; then
+  echo "    pre-fix kernel finished this time (the hazard is timing dependent)"
+else
+  echo "    pre-fix kernel did not finish (exit $?): $(tail -n 1 "$OUT/xfix_prefix_repro.log")"
+fi
+
 # 1. packed fp32x2 softmax / dS arithmetic (FFMA2 / FADD2 / FMUL2)
 step tests_f32x2 420 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
 step perf_f32x2 120 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
