@@ -27,15 +27,8 @@ step() {   # step <name> <timeout_s> <env...> -- <cmd...>
 step perf_default 120 S=32768 -- python tools/gpu_time_passes.py
 
 # 0b. the round-1 hang and its fix (dQ pass, empty work items): the fixed kernel must finish and match the oracle;
-#     the pre-fix kernel is EXPECTED to hang sooner or later (timeout 40 s; reported, not counted as a failure)
+#     (the pre-fix reproduction, which is EXPECTED to hang, runs as the very last step of this script)
 step xfix_fixed 180 -- python tools/gpu_repro_xfix.py
-echo "=== xfix_prefix_repro (LCA_B200_NO_XFIX=1; a timeout here CONFIRMS the diagnosis)"
-if LCA_B200_NO_XFIX=1 timeout 40 python tools/gpu_repro_xfix.py --no-check > "$OUT/xfix_prefix_repro.log" 2>&1; then
-  echo "    pre-fix kernel finished this time (the hazard is timing dependent)"
-else
-  echo "    pre-fix kernel did not finish (exit $?): $(tail -n 1 "$OUT/xfix_prefix_repro.log")"
-fi
-
 # 1. packed fp32x2 softmax / dS arithmetic (FFMA2 / FADD2 / FMUL2)
 step tests_f32x2 420 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu
 step perf_f32x2 120 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
@@ -73,5 +66,12 @@ grep -h '"name"' "$OUT"/perf_*.log 2>/dev/null | sed 's/^/  /' > "$OUT/summary.t
 for f in "$OUT"/perf_*.log; do echo "$(basename "$f" .log): $(grep -h '"name"' "$f" | python -c '
 import sys, json
 print("  ".join("%s %.3f ms" % (d["name"].split("(")[0], d["ms"]) for d in map(json.loads, sys.stdin)))')"; done | tee -a "$OUT/summary.txt"
+# last on purpose: a kernel that is expected to hang is killed after 40 s; nothing else depends on the GPU afterwards
+echo "=== xfix_prefix_repro (LCA_B200_NO_XFIX=1; a timeout here CONFIRMS the diagnosis)"
+if LCA_B200_NO_XFIX=1 timeout -s KILL 40 python tools/gpu_repro_xfix.py --no-check > "$OUT/xfix_prefix_repro.log" 2>&1; then
+  echo "    pre-fix kernel finished this time (the hazard is timing dependent)"
+else
+  echo "    pre-fix kernel did not finish (exit $?): $(tail -n 1 "$OUT/xfix_prefix_repro.log")"
+fi
 echo "failed steps: $fail"
 exit $fail
