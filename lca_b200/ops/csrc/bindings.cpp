@@ -494,6 +494,7 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
 // visible tiles are an index interval [lo, hi]: O(1).  Such launches take the kXfix instantiation of the dQ pass.
 static bool has_empty_stationary_tile(const BwdParams& p) {
   constexpr int64_t BXr = 128, BYr = 64;
+  if (p.x_pos_stride <= 0 || p.y_pos_stride <= 0) return false;      // not a layout this library produces
   for (int xi = 0; xi < p.n_xseg; ++xi) {
     const XSegD& xs = p.xseg[xi];
     const int64_t ntx = (xs.nrows + BXr - 1) / BXr;
