@@ -135,7 +135,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }  // namespace
 
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
-template <int kD, bool kBf16, int kPolyEvery>
+// kPk: packed fp32x2 softmax arithmetic (FFMA2 / FADD2), same code as the kPk variant of fmha_fwd_sm100.cu on 64 columns
+template <int kD, bool kBf16, int kPolyEvery, bool kPk>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
@@ -422,7 +423,31 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid
         const float sub = (m == -INFINITY) ? 0.f : m;
         // ---- P = exp2(x*mul - m), row sum, pack, store over the first 32 columns of this stage
         float rs = 0.f;
-        if (general) {
+        if constexpr (kPk) {
+          const uint64_t mul2 = ptx::pack_f32x2(mul, mul), nsub2 = ptx::pack_f32x2(-sub, -sub);
+          uint64_t acc_a = ptx::pack_f32x2(0.f, 0.f), acc_b = acc_a;
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            const uint64_t x =
+                ptx::fma_f32x2(ptx::pack_f32x2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), mul2, nsub2);
+            float p0, p1;
+            // masked tiles carry -inf logits: the polynomial needs finite arguments, so it only runs on unmasked tiles
+            if (kPolyEvery > 0 && ((c >> 1) % (kPolyEvery > 0 ? kPolyEvery : 1)) == 0 && !general) {
+              ptx::ex2_poly_x2(x, p0, p1);
+            } else {
+              float x0, x1;
+              ptx::unpack_f32x2(x, x0, x1);
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            if (c & 2) acc_b = ptx::add_f32x2(acc_b, ptx::pack_f32x2(p0, p1));
+            else acc_a = ptx::add_f32x2(acc_a, ptx::pack_f32x2(p0, p1));
+            v[c >> 1] = pack2<kBf16>(p0, p1);
+          }
+          float s0, s1;
+          ptx::unpack_f32x2(ptx::add_f32x2(acc_a, acc_b), s0, s1);
+          rs = s0 + s1;
+        } else if (general) {
 #pragma unroll
           for (int c = 0; c < 64; c += 2) {
             const float p0 = ex2(fmaf(__uint_as_float(v[c]), mul, -sub));
@@ -533,10 +558,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_bn64_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly>
+template <int kD, bool kBf16, int kPoly, bool kPk = false>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_bn64_kernel<kD, kBf16, kPoly>;
+  auto kern = fmha_fwd_bn64_kernel<kD, kBf16, kPoly, kPk>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -553,6 +578,14 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  if (p.f32x2) {
+    switch (p.poly_every) {
+      case 0: return launch_impl<kD, kBf16, 0, true>(p, num_sms, stream);
+      case 3: return launch_impl<kD, kBf16, 3, true>(p, num_sms, stream);
+      case 4: return launch_impl<kD, kBf16, 4, true>(p, num_sms, stream);
+      default: return launch_impl<kD, kBf16, 6, true>(p, num_sms, stream);
+    }
+  }
   switch (p.poly_every) {
     case 0: return launch_impl<kD, kBf16, 0>(p, num_sms, stream);
     case 3: return launch_impl<kD, kBf16, 3>(p, num_sms, stream);

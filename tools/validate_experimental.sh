@@ -44,6 +44,9 @@ step perf_d64_default 120 S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
 step tests_bn64 420 LCA_B200_FWD_BN64=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "fwd or module or padded or varlen or util"
 step perf_bn64 120 LCA_B200_FWD_BN64=1 S=32768 -- python tools/gpu_time_passes.py
 step perf_bn64_poly3 120 LCA_B200_FWD_BN64=1 LCA_B200_POLY_EVERY=3 S=32768 -- python tools/gpu_time_passes.py
+step tests_bn64_f32x2 420 LCA_B200_FWD_BN64=1 LCA_B200_F32X2=1 -- python -m pytest tests/test_native_gpu.py -x -q -m gpu -k "fwd or module or padded or varlen"
+step perf_bn64_f32x2 120 LCA_B200_FWD_BN64=1 LCA_B200_F32X2=1 S=32768 -- python tools/gpu_time_passes.py
+step perf_bn64_f32x2_poly3 120 LCA_B200_FWD_BN64=1 LCA_B200_F32X2=1 LCA_B200_POLY_EVERY=3 S=32768 -- python tools/gpu_time_passes.py
 step perf_bn64_d64 120 LCA_B200_FWD_BN64=1 LCA_B200_POLY_EVERY=3 S=32768 D=64 H=16 -- python tools/gpu_time_passes.py
 
 # 1b. backward with both element-wise warpgroups on every streamed tile (halves the per-tile critical path)
