@@ -1,8 +1,8 @@
 #!/usr/bin/env bash
 # First GPU call of a round: validate the opt-in (template-gated) kernel variants that were written without hardware
-# and measure them against the default build.  One GPU, ~15 minutes.  Everything lands in gpurun_out/experimental/.
+# and measure them against the default build.  One GPU, ~30 minutes.  Everything lands in gpurun_out/experimental/.
 #
-#   gpurun --timeout 1800 -- 'bash tools/validate_experimental.sh'
+#   gpurun --timeout 2700 -- 'bash tools/validate_experimental.sh'
 #
 # Each step runs under its own timeout so a hung kernel cannot eat the box.  Exit code = number of failed steps.
 set -u
