@@ -488,13 +488,20 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
 // ------------------------------------------------------------------------------------ fmha bwd
 // One pass of the backward (see fmha_bwd_sm100.cu).  x0/x1 stationary, y0/y1 streamed.
 // xsegs[i] = {row0, nrows, pos0, group, o_row0 [, flag, o_base0, o_base1, o_sig]};  ysegs[i] = {row0, nrows, pos0, flag, group}
-// True when some 128-row stationary tile of the launch has NO visible streamed tile under the kernel's own skipping
-// rule (TileIter in fmha_bwd_sm100.cu: a streamed 64-row tile [ka, kb] of the same group is visited unless
-// ka - xmax > wr or xmin - kb > wl).  ka and kb grow with the tile index, so per (stationary tile, streamed segment) the
-// visible tiles are an index interval [lo, hi]: O(1).  Such launches take the kXfix instantiation of the dQ pass.
-static bool has_empty_stationary_tile(const BwdParams& p) {
+// Counts the 128-row stationary tiles of a launch that have NO visible streamed tile, and those with at most two, under
+// the kernel's own skipping rule (TileIter in fmha_bwd_sm100.cu: a streamed 64-row tile [ka, kb] of the same group is
+// visited unless ka - xmax > wr or xmin - kb > wl).  ka and kb grow with the tile index, so per (stationary tile,
+// streamed segment) the visible tiles are an index interval [lo, hi]: O(1).
+// Why "at most two": the MMA warp issues the first two T GEMM pairs of a work item in its prologue without any
+// warpgroup participation and releases x_empty when the LAST one is issued -- so for such items X can be reloaded (and
+// x_full advance) before a warpgroup that is still in the previous epilogue has waited for this item's phase.
+struct SmallTileCount {
+  int64_t empty = 0, small = 0;      // small includes empty
+};
+static SmallTileCount count_small_stationary_tiles(const BwdParams& p) {
   constexpr int64_t BXr = 128, BYr = 64;
-  if (p.x_pos_stride <= 0 || p.y_pos_stride <= 0) return false;      // not a layout this library produces
+  SmallTileCount out;
+  if (p.x_pos_stride <= 0 || p.y_pos_stride <= 0) return out;      // not a layout this library produces
   for (int xi = 0; xi < p.n_xseg; ++xi) {
     const XSegD& xs = p.xseg[xi];
     const int64_t ntx = (xs.nrows + BXr - 1) / BXr;
@@ -502,8 +509,8 @@ static bool has_empty_stationary_tile(const BwdParams& p) {
       const int64_t rows = std::min<int64_t>(BXr, xs.nrows - t * BXr);
       const int64_t xmin = xs.pos0 + t * BXr * p.x_pos_stride;
       const int64_t xmax = xmin + (rows - 1) * p.x_pos_stride;
-      bool visible = false;
-      for (int yi = 0; yi < p.n_yseg && !visible; ++yi) {
+      int64_t visible = 0;
+      for (int yi = 0; yi < p.n_yseg && visible <= 2; ++yi) {
         const KSegD& ys = p.yseg[yi];
         if (ys.group != xs.group || ys.nrows <= 0) continue;
         const int64_t nt = (ys.nrows + BYr - 1) / BYr;
@@ -523,16 +530,17 @@ static bool has_empty_stationary_tile(const BwdParams& p) {
           int64_t k = num <= 0 ? 0 : (num + step - 1) / step;
           lo = std::min<int64_t>(k, nt - 1);                     // the (possibly partial) last tile reaches kb_last >= need
         }
-        visible = lo <= hi;
+        if (lo <= hi) visible += hi - lo + 1;
       }
-      if (!visible) return true;
+      if (visible == 0) ++out.empty;
+      if (visible <= 2) ++out.small;
     }
   }
-  return false;
+  return out;
 }
 
 // host-only entry for the CPU test-suite: xsegs[i] = {nrows, pos0, group}, ysegs[i] = {nrows, pos0, group}
-bool debug_has_empty_tile(const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
+std::vector<int64_t> debug_count_small_tiles(const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
                           int64_t x_pos_stride, int64_t y_pos_stride, int64_t wl, int64_t wr) {
   BwdParams p;
   std::memset(&p, 0, sizeof(p));
@@ -553,7 +561,8 @@ bool debug_has_empty_tile(const std::vector<std::vector<int64_t>>& xsegs, const 
   p.y_pos_stride = static_cast<int>(y_pos_stride);
   p.wl = static_cast<int>(wl);
   p.wr = static_cast<int>(wr);
-  return has_empty_stationary_tile(p);
+  const SmallTileCount c = count_small_stationary_tiles(p);
+  return {c.empty, c.small};
 }
 
 static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
@@ -650,7 +659,13 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   p.out_mode = static_cast<int>(out_mode);
   // LCA_B200_NO_XFIX=1 keeps the pre-fix kernel even for launches with empty work items (only to reproduce the hang)
   static const bool no_xfix = [] { const char* v = std::getenv("LCA_B200_NO_XFIX"); return v && std::atoi(v) == 1; }();
-  if (!is_dkv && !no_xfix) p.xfix = has_empty_stationary_tile(p) ? 1 : 0;
+  if (!is_dkv && !no_xfix) {
+    // kXfix whenever a CTA could meet such an item right behind another work item: any empty tile (they come in long
+    // runs in the collective zigzag/stripe ring), or more short items than CTAs (plain causal self-attention has one
+    // two-tile item per (batch, head), each on its own CTA in the last scheduling round: validated kernel stays)
+    const SmallTileCount c = count_small_stationary_tiles(p);
+    p.xfix = (c.empty > 0 || c.small * p.B * p.Hx > num_sms()) ? 1 : 0;
+  }
 }
 
 static void fmha_bwd_pass_impl(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
@@ -841,7 +856,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
-  m.def("debug_has_empty_tile", &lca::debug_has_empty_tile, "host-only: does a dQ-pass launch contain an empty work item?");
+  m.def("debug_count_small_tiles", &lca::debug_count_small_tiles,
+        "host-only: {stationary tiles with no visible streamed tile, with at most two} of a dQ-pass launch");
   m.def("set_next_dropout", &lca::set_next_dropout, "EXPERIMENTAL: {p8, seed, head_offset} for the next fused launch");
   m.def("fmha_fwd_drop", &lca::fmha_fwd_drop, "EXPERIMENTAL: forward with coordinate-keyed dropout");
   m.def("fmha_bwd_pass_drop", &lca::fmha_bwd_pass_drop, "EXPERIMENTAL: backward pass with coordinate-keyed dropout");

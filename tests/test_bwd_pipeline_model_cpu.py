@@ -244,14 +244,17 @@ def test_backward_pipeline_protocol(split, is_dkv, seed):
     BwdModel(work, split, is_dkv, seed).run()
 
 
-def test_dq_pass_without_xfix_can_miss_a_phase():
-    """The hazard kXfix removes, made deterministic: an empty work item right after a non-empty one while the
-    element-wise warpgroups are still in the previous epilogue.  ``x_empty`` is released by the MMA warp alone, the
-    producer reloads X, ``x_full`` completes two phases before the warpgroup's one-bit parity wait -> it blocks forever."""
+@pytest.mark.parametrize("work", [[2, 0, 1, 1], [3, 2, 2, 2], [3, 1, 1, 1]])
+def test_dq_pass_without_xfix_can_miss_a_phase(work):
+    """The hazard kXfix removes, made deterministic: a work item whose T GEMMs are all issued in the MMA warp's
+    prologue (no visible streamed tile, or at most two) right behind another item, while the element-wise warpgroups
+    are still in the previous epilogue.  ``x_empty`` is released by the MMA warp alone, the producer reloads X,
+    ``x_full`` completes two phases before the warpgroup's one-bit parity wait -> it blocks forever.  With kXfix every
+    element-wise warp also arrives on ``x_empty``, so the same schedule completes."""
     MBar.TIMEOUT = 1.5
     try:
         with pytest.raises(AssertionError):
-            BwdModel([2, 0, 1, 1], False, False, 0, xfix=False, slow_epilogue=0.3).run()
-        BwdModel([2, 0, 1, 1], False, False, 0, xfix=True, slow_epilogue=0.3).run()
+            BwdModel(work, False, False, 0, xfix=False, slow_epilogue=0.3).run()
+        BwdModel(work, False, False, 0, xfix=True, slow_epilogue=0.3).run()
     finally:
         MBar.TIMEOUT = 20.0
