@@ -664,7 +664,7 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
     // runs in the collective zigzag/stripe ring), or more short items than CTAs (plain causal self-attention has one
     // two-tile item per (batch, head), each on its own CTA in the last scheduling round: validated kernel stays)
     const SmallTileCount c = count_small_stationary_tiles(p);
-    p.xfix = (c.empty > 0 || c.small * p.B * p.Hx > num_sms()) ? 1 : 0;
+    p.xfix = (c.empty > 0 || c.small * p.B * p.Hx > num_sms() - 16) ? 1 : 0;   // up to 16 SMs may run push CTAs
   }
 }
 
