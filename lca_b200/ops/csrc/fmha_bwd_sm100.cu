@@ -194,6 +194,8 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit, bool kMc, bool kXfix>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
+  // every opt-in variant carries the x_empty fix; only the hardware-validated default keeps the old release rule
+  constexpr bool kXf = (kXfix || kDyn || kPk || kDrop || kSplit || kMc) && !kIsDKV;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
     comm_cta<kMc>(p.comm);
     if constexpr (!kDyn) return;
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       }
     }
     mbar_init(x_full, 1);
-    mbar_init(x_empty, (kXfix && !kIsDKV) ? 9 : 1);
+    mbar_init(x_empty, kXf ? 9 : 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 8);
     for (int s = 0; s < 2; ++s) {
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         // acquired the arrival flag before issuing the tile's TMA, so x_full orders our reads after the push
         mbar_wait(x_full, xcw & 1);
         ++xcw;
-        if constexpr (kXfix) {
+        if constexpr (kXf) {
           if (lane == 0) mbar_arrive(x_empty);     // this warp has consumed the phase: X may be reloaded
         }
         if (row_ok) {
@@ -704,8 +706,6 @@ static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cud
   if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
     return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
-  if (p.xfix && !is_dkv)              // dQ pass with work items that see no streamed tile (see kXfix above)
-    return launch_impl<kD, kBf16, false, false, false, false, false, false, true>(p, num_sms, stream);
   if (p.split && !p.dyn_sched) {      // experimental: both warpgroups on every streamed tile (static schedule only)
     if (p.f32x2)
       return is_dkv ? launch_impl<kD, kBf16, true, false, true, false, true>(p, num_sms, stream)
@@ -718,6 +718,8 @@ static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cud
                   : launch_impl<kD, kBf16, false, false, true>(p, num_sms, stream);
   if (p.dyn_sched)
     return is_dkv ? launch_impl<kD, kBf16, true, true>(p, num_sms, stream) : launch_impl<kD, kBf16, false, true>(p, num_sms, stream);
+  if (p.xfix && !is_dkv)              // dQ pass with short / empty work items (see kXfix above); every opt-in variant has it built in
+    return launch_impl<kD, kBf16, false, false, false, false, false, false, true>(p, num_sms, stream);
   return is_dkv ? launch_impl<kD, kBf16, true, false>(p, num_sms, stream) : launch_impl<kD, kBf16, false, false>(p, num_sms, stream);
 }
 
