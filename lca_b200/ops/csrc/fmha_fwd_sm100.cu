@@ -154,6 +154,10 @@ struct Bars {
 template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk, bool kDrop, bool kMc>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
+  // opt-in variants hand the Q tiles of an EMPTY work item (no visible K/V tile) back through o_full, so q_full can
+  // never complete two phases under the MMA warp's parity wait (docs/ROUND2_PLAN.md, "Robustness item"); the
+  // hardware-validated default keeps its original rule (the warpgroup waits q_full itself)
+  constexpr bool kQf = kDyn || kPk || kDrop || kMc;
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
     comm_cta<kMc>(p.comm);
     if constexpr (!kDyn) return;
@@ -321,7 +325,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           mbar_wait(B.q_full[t], qc[t] & 1);
           ++qc[t];
         }
-        if (!have) continue;
+        if (!have) {
+          if constexpr (kQf) {
+            for (int t = 0; t < nt; ++t) mma_commit(B.o_full[t]);
+          }
+          continue;
+        }
         // first tile: S_t = Q_t K_0^T
         uint32_t kslot = kvc % C::STAGES;
         mbar_wait(B.kv_full + 8 * kslot, (kvc / C::STAGES) & 1);
@@ -598,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       }
       // ---- epilogue: O / l -> 16-bit -> smem (XOR-swizzled 16B chunks) -> coalesced global stores
       uint8_t* stage = smem_gen + C::OFF_Q + t * C::TILE_BYTES;
-      if (j > 0) {
+      if (j > 0 || kQf) {
         mbar_wait(B.o_full[t], oc & 1);
         ++oc;
         tc_fence_after();
