@@ -251,7 +251,7 @@ def test_dq_pass_without_xfix_can_miss_a_phase(work):
     are still in the previous epilogue.  ``x_empty`` is released by the MMA warp alone, the producer reloads X,
     ``x_full`` completes two phases before the warpgroup's one-bit parity wait -> it blocks forever.  With kXfix every
     element-wise warp also arrives on ``x_empty``, so the same schedule completes."""
-    MBar.TIMEOUT = 1.5
+    MBar.TIMEOUT = 3.0
     try:
         with pytest.raises(AssertionError):
             BwdModel(work, False, False, 0, xfix=False, slow_epilogue=0.3).run()

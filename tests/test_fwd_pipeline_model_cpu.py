@@ -202,7 +202,7 @@ def test_forward_empty_items_without_o_full_handback_need_a_prompt_mma_warp():
     releases ``q_empty``) an MMA warp that lagged a whole work item would see ``q_full`` complete two phases under its
     one-bit parity wait.  The model forces that lag; on hardware the MMA warp reaches the wait microseconds before the Q
     tile can be reloaded, which is why the validated default has never shown it."""
-    MBar.TIMEOUT = 1.5
+    MBar.TIMEOUT = 3.0
     try:
         with pytest.raises(AssertionError):
             FwdModel([(1, 1), (1, 0), (1, 0), (1, 1)], 0, qf=False, slow_mma=0.4).run()
