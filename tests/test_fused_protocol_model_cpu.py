@@ -1,0 +1,188 @@
+"""Executable model of the cross-rank protocol of the fused USP kernels (``csrc/usp_comm.cuh`` +
+``parallel/fused_engine.py``): ready-to-receive handshake, arrival counters, owner completion counters, all of them
+monotonic "epochs" that are never reset; three kernels per training step (forward, backward dQ pass with the pushes,
+backward dK/dV pass without a comm role) on every rank of a U x R mesh, several steps back to back.
+
+Each rank runs its kernels in stream order; inside a kernel a push thread (the comm CTAs) and a compute thread (the
+attention CTAs) run concurrently, and the ranks drift apart at random.  Staging buffers carry the epoch of their
+contents: a reader must find exactly the current call's data (never a stale or a too-new version), i.e. the model checks
+that no rank can overwrite a peer's staging while that peer may still read the previous contents, and that nothing
+deadlocks.  Both push flavours are modelled: the unicast loop and the NVLS-style broadcast (wait for ALL ready flags,
+one write, then all arrival counters)."""
+import random
+import threading
+import time
+
+import pytest
+
+KV, Q, RTR, ODONE, DKV, QA = 0, 16, 32, 48, 49, 64
+
+
+class Sig:
+    """Signal pad of one rank: monotonic counters, waiters block until a slot reaches a target."""
+
+    def __init__(self):
+        self.v = [0] * 96
+        self.cv = threading.Condition()
+
+    def add(self, slot, n=1):
+        with self.cv:
+            self.v[slot] += n
+            self.cv.notify_all()
+
+    def store_max(self, slot, val):
+        with self.cv:
+            self.v[slot] = max(self.v[slot], val)
+            self.cv.notify_all()
+
+    def wait_ge(self, slot, target, timeout=20.0):
+        with self.cv:
+            assert self.cv.wait_for(lambda: self.v[slot] >= target, timeout), f"deadlock: slot {slot} < {target}"
+
+
+class Mesh:
+    def __init__(self, U, R, n_comm, broadcast, seed):
+        self.U, self.R, self.P, self.n_comm, self.broadcast = U, R, U * R, n_comm, broadcast
+        self.rng = random.Random(seed)
+        self.sig = [Sig() for _ in range(self.P)]
+        self.lock = threading.Lock()
+        # staging[dst][(cls, src)] = epoch of the contents;  readers[dst][(cls, src)] = epoch currently being read
+        self.staging = [dict() for _ in range(self.P)]
+        self.reading = [dict() for _ in range(self.P)]
+        self.errors = []
+
+    def jitter(self, scale=3e-4):
+        time.sleep(self.rng.random() * scale)
+
+    def check(self, cond, msg):
+        if not cond:
+            self.errors.append(msg)
+            raise AssertionError(msg)
+
+    # ------------------------------------------------------------------ one kernel on one rank
+    def push(self, me, epoch, classes_all, classes_ring):
+        """comm CTAs: classes_all go to every rank, classes_ring (Ulysses Q) to the ranks of my ring index."""
+        u, r = me % self.U, me // self.U
+        for t in range(self.P):
+            self.sig[t].store_max(RTR + me, epoch)                    # my staging is free for this call
+        order = [(me + i) % self.P for i in range(self.P)]
+        if self.broadcast and self.U == 1:
+            for d in order:
+                self.sig[me].wait_ge(RTR + d, epoch)
+            self.jitter()
+            with self.lock:
+                for d in range(self.P):
+                    for c in classes_all:
+                        self._write(d, (c, me), epoch)
+            for d in order:
+                self._signal(d, me, u, d // self.U == r)
+            return
+        for d in order:
+            self.sig[me].wait_ge(RTR + d, epoch)
+            self.jitter()
+            with self.lock:
+                for c in classes_all:
+                    self._write(d, (c, me), epoch)
+                if d // self.U == r:
+                    for c in classes_ring:
+                        self._write(d, (c, me), epoch)
+            self._signal(d, me, u, d // self.U == r)
+
+    def _write(self, dst, key, epoch):
+        rd = self.reading[dst].get(key)
+        self.check(rd is None, f"rank {key[1]} overwrites staging {key} of rank {dst} (epoch {epoch}) while it reads epoch {rd}")
+        self.staging[dst][key] = epoch
+
+    def _signal(self, d, me, u, same_ring):
+        self.sig[d].add(KV + me, self.n_comm)
+        if same_ring:
+            self.sig[d].add(Q + u, self.n_comm)
+        self.sig[d].add(QA + me, self.n_comm)
+
+    def consume(self, me, epoch, needs):
+        """compute CTAs: needs = [(flag slot, (cls, src))...] in visiting order."""
+        for slot, key in needs:
+            self.sig[me].wait_ge(slot, epoch * self.n_comm)
+            with self.lock:
+                got = self.staging[me].get(key)
+                self.check(got == epoch, f"rank {me} reads {key}: epoch {got}, wants {epoch}")
+                self.reading[me][key] = epoch
+            self.jitter()
+            with self.lock:
+                self.reading[me][key] = None
+
+    def kernel(self, me, epoch, classes_all, classes_ring, needs, owners, done_slot, target):
+        """One fused launch: push thread || compute thread; the launch ends when both are done and, if this rank owns
+        outputs produced elsewhere, when its completion counter reached the host-computed target."""
+        res = {}
+
+        def guard(fn, *a):
+            try:
+                fn(*a)
+            except Exception as e:  # noqa: BLE001
+                res[fn.__name__] = e
+
+        th = []
+        if classes_all or classes_ring:
+            th.append(threading.Thread(target=guard, args=(self.push, me, epoch, classes_all, classes_ring), daemon=True))
+        th.append(threading.Thread(target=guard, args=(self.consume, me, epoch, needs), daemon=True))
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(60)
+            assert not t.is_alive(), f"deadlock in kernel of rank {me}, epoch {epoch}: {res}"
+        assert not res, res
+        for o in owners:                                              # tiles scattered to the token owners
+            self.sig[o].add(done_slot, 1)
+        if target is not None:
+            self.sig[me].wait_ge(done_slot, target)
+
+    # ------------------------------------------------------------------ a rank's stream
+    def rank(self, me, steps):
+        U, R, P = self.U, self.R, self.P
+        u, r = me % U, me // U
+        ring_block = [r * U + x for x in range(U)]                    # the ranks whose queries I compute (my ring index)
+        epoch, o_total, dkv_total = 0, 0, 0
+        for _ in range(steps):
+            self.jitter(2e-3)                                         # host-side drift between ranks
+            # forward: K/V to everyone, Q to my Ulysses peers; I read Q of my ring block and every K/V
+            epoch += 1
+            needs = ([(Q + x, ("q", r * U + x)) for x in range(U)] if U > 1 else []) + \
+                    [(KV + s, ("kv", s)) for s in [(me + i) % P for i in range(P)]]
+            if U > 1:
+                o_total += U
+            self.kernel(me, epoch, ["kv"], ["q"] if U > 1 else [], needs, ring_block if U > 1 else [], ODONE,
+                        o_total if U > 1 else None)
+            # backward, dQ pass: q/dO/stats and K/V to EVERY rank; dQ tiles go to the owners in my ring block
+            epoch += 1
+            needs = [(QA + s, ("qa", s)) for s in ring_block] + [(KV + s, ("kv", s)) for s in range(P)]
+            o_total += U
+            self.kernel(me, epoch, ["kv", "qa"], [], needs, ring_block, ODONE, o_total)
+            # backward, dK/dV pass: no comm role; reads what pass 1 delivered; dK/dV tiles go to the owners
+            needs = [(KV + s, ("kv", s)) for s in ring_block] + [(QA + s, ("qa", s)) for s in range(P)]
+            dkv_total += U
+            self.kernel(me, epoch, [], [], needs, ring_block, DKV, dkv_total)    # target = the host's symm_wait
+
+
+@pytest.mark.parametrize("U,R", [(1, 2), (2, 1), (2, 2), (1, 8), (4, 2)])
+@pytest.mark.parametrize("broadcast", [False, True])
+def test_fused_cross_rank_protocol(U, R, broadcast):
+    if broadcast and U != 1:
+        pytest.skip("the broadcast push exists for pure-ring meshes only")
+    mesh = Mesh(U, R, n_comm=2, broadcast=broadcast, seed=U * 10 + R)
+    res = {}
+
+    def guard(me):
+        try:
+            mesh.rank(me, steps=3)
+        except Exception as e:  # noqa: BLE001
+            res[me] = e
+
+    threads = [threading.Thread(target=guard, args=(me,), daemon=True) for me in range(U * R)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+        assert not t.is_alive(), f"deadlock: {res}"
+    assert not res, res
+    assert not mesh.errors, mesh.errors
