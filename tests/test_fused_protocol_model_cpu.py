@@ -35,14 +35,17 @@ class Sig:
             self.v[slot] = max(self.v[slot], val)
             self.cv.notify_all()
 
-    def wait_ge(self, slot, target, timeout=20.0):
+    TIMEOUT = 20.0
+
+    def wait_ge(self, slot, target):
         with self.cv:
-            assert self.cv.wait_for(lambda: self.v[slot] >= target, timeout), f"deadlock: slot {slot} < {target}"
+            assert self.cv.wait_for(lambda: self.v[slot] >= target, Sig.TIMEOUT), f"deadlock: slot {slot} < {target}"
 
 
 class Mesh:
-    def __init__(self, U, R, n_comm, broadcast, seed):
+    def __init__(self, U, R, n_comm, broadcast, seed, use_rtr=True):
         self.U, self.R, self.P, self.n_comm, self.broadcast = U, R, U * R, n_comm, broadcast
+        self.use_rtr = use_rtr
         self.rng = random.Random(seed)
         self.sig = [Sig() for _ in range(self.P)]
         self.lock = threading.Lock()
@@ -68,7 +71,8 @@ class Mesh:
         order = [(me + i) % self.P for i in range(self.P)]
         if self.broadcast and self.U == 1:
             for d in order:
-                self.sig[me].wait_ge(RTR + d, epoch)
+                if self.use_rtr:
+                    self.sig[me].wait_ge(RTR + d, epoch)
             self.jitter()
             with self.lock:
                 for d in range(self.P):
@@ -78,7 +82,8 @@ class Mesh:
                 self._signal(d, me, u, d // self.U == r)
             return
         for d in order:
-            self.sig[me].wait_ge(RTR + d, epoch)
+            if self.use_rtr:
+                self.sig[me].wait_ge(RTR + d, epoch)
             self.jitter()
             with self.lock:
                 for c in classes_all:
@@ -186,3 +191,25 @@ def test_fused_cross_rank_protocol(U, R, broadcast):
         assert not t.is_alive(), f"deadlock: {res}"
     assert not res, res
     assert not mesh.errors, mesh.errors
+
+
+def test_model_detects_a_missing_ready_to_receive_handshake():
+    """Negative control: without the RTR wait a fast rank overwrites a slow peer's staging (or the peer reads data of
+    the wrong epoch) -- the model must notice."""
+    mesh = Mesh(1, 4, n_comm=2, broadcast=False, seed=3, use_rtr=False)
+    res = {}
+    Sig.TIMEOUT = 2.0
+
+    def guard(me):
+        try:
+            mesh.rank(me, steps=4)
+        except Exception as e:  # noqa: BLE001
+            res[me] = e
+
+    threads = [threading.Thread(target=guard, args=(me,), daemon=True) for me in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    Sig.TIMEOUT = 20.0
+    assert mesh.errors, "the model did not detect the missing handshake"
