@@ -46,3 +46,19 @@ def test_utils_timer_and_logger():
         sum(range(1000))
     assert t.ms >= 0 and t.max_over_ranks() == t.ms
     get_logger().warning("logger ok")
+
+
+def test_pipeline_timing_model_reproduces_the_measured_utilisations():
+    """tools/pipeline_sim.py: solving for the element-wise time must give back the measured tensor-pipe utilisation,
+    and the structural variants must never predict less than the pipelines they replace."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pipeline_sim", os.path.join(ROOT, "tools", "pipeline_sim.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    wf = m.solve(m.fwd_default, 0.63)
+    assert abs(m.fwd_default(wf) - 0.63) < 5e-3 and 1500 < wf < 2600
+    assert m.fwd_bn64(wf / 2 + 100) > m.fwd_default(wf)
+    for a_dur, target in ((256, 0.66), (512, 0.70)):
+        w = m.solve(lambda x: m.bwd(x, 512, a_dur, False), target)
+        assert abs(m.bwd(w, 512, a_dur, False) - target) < 5e-3
+        assert m.bwd(w, 512, a_dur, True) > target
