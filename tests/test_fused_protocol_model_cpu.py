@@ -43,7 +43,8 @@ class Sig:
 
 
 class Mesh:
-    def __init__(self, U, R, n_comm, broadcast, seed, use_rtr=True):
+    def __init__(self, U, R, n_comm, broadcast, seed, use_rtr=True, slow_reader=None):
+        self.slow_reader = slow_reader              # (rank, seconds): that rank dwells on every staging read
         self.U, self.R, self.P, self.n_comm, self.broadcast = U, R, U * R, n_comm, broadcast
         self.use_rtr = use_rtr
         self.rng = random.Random(seed)
@@ -113,6 +114,8 @@ class Mesh:
                 self.check(got == epoch, f"rank {me} reads {key}: epoch {got}, wants {epoch}")
                 self.reading[me][key] = epoch
             self.jitter()
+            if self.slow_reader is not None and self.slow_reader[0] == me:
+                time.sleep(self.slow_reader[1])
             with self.lock:
                 self.reading[me][key] = None
 
@@ -196,7 +199,7 @@ def test_fused_cross_rank_protocol(U, R, broadcast):
 def test_model_detects_a_missing_ready_to_receive_handshake():
     """Negative control: without the RTR wait a fast rank overwrites a slow peer's staging (or the peer reads data of
     the wrong epoch) -- the model must notice."""
-    mesh = Mesh(1, 4, n_comm=2, broadcast=False, seed=3, use_rtr=False)
+    mesh = Mesh(1, 4, n_comm=2, broadcast=False, seed=3, use_rtr=False, slow_reader=(0, 0.3))
     res = {}
     Sig.TIMEOUT = 2.0
 
