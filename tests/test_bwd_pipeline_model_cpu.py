@@ -253,8 +253,13 @@ def test_dq_pass_without_xfix_can_miss_a_phase(work):
     element-wise warp also arrives on ``x_empty``, so the same schedule completes."""
     MBar.TIMEOUT = 3.0
     try:
-        with pytest.raises(AssertionError):
-            BwdModel(work, False, False, 0, xfix=False, slow_epilogue=0.3).run()
+        for attempt in range(3):            # the forced lag is generous, but thread scheduling is not ours: retry
+            try:
+                BwdModel(work, False, False, attempt, xfix=False, slow_epilogue=0.3).run()
+            except AssertionError:
+                break
+        else:
+            pytest.fail("the pre-fix protocol survived three forced-lag runs")
         BwdModel(work, False, False, 0, xfix=True, slow_epilogue=0.3).run()
     finally:
         MBar.TIMEOUT = 20.0

@@ -204,8 +204,13 @@ def test_forward_empty_items_without_o_full_handback_need_a_prompt_mma_warp():
     tile can be reloaded, which is why the validated default has never shown it."""
     MBar.TIMEOUT = 3.0
     try:
-        with pytest.raises(AssertionError):
-            FwdModel([(1, 1), (1, 0), (1, 0), (1, 1)], 0, qf=False, slow_mma=0.4).run()
+        for attempt in range(3):
+            try:
+                FwdModel([(1, 1), (1, 0), (1, 0), (1, 1)], attempt, qf=False, slow_mma=0.4).run()
+            except AssertionError:
+                break
+        else:
+            pytest.fail("the default rule survived three forced-lag runs")
         FwdModel([(1, 1), (1, 0), (1, 0), (1, 1)], 0, qf=True, slow_mma=0.4).run()
     finally:
         MBar.TIMEOUT = 20.0
