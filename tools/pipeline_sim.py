@@ -120,6 +120,15 @@ def main():
                          (0.7, "-30 % (packed + poly 1/3)"), (0.6, "-40 %")]:
         W = wf * scale
         w(f"| {W:.0f} clk ({label}) | {fwd_default(W):.2f} | {fwd_bn64(W / 2 + 100):.2f} |")
+    w("\n## Forward at head_dim 64 (QK / PV take half the clocks, the softmax does not shrink)\n")
+    w("Measured: 490 TFLOPS = 0.28 of burst peak at D=64.  The implied softmax time from the D=128 fit predicts")
+    w(f"{fwd_default(wf, 256, 256):.2f} for the default pipeline (measured 0.28: the D=64 kernel is even more softmax-bound than the")
+    w("latency model says, i.e. throughput-bound on MUFU/issue), and the table shows that only a faster softmax helps there:\n")
+    w("| softmax time per 128 columns | default pipeline, D=64 | BN64 pipeline, D=64 |")
+    w("|---|---|---|")
+    for scale in (1.0, 0.7, 0.5):
+        W = wf * scale
+        w(f"| {W:.0f} clk | {fwd_default(W, 256, 256):.2f} | {fwd_bn64(W / 2 + 100, 128, 128):.2f} |")
     w("\n## Backward: alternating warpgroups (default) vs both warpgroups on every tile (`kSplit`)\n")
     w("| element-wise time per 64 columns | dQ default | dQ split | dK/dV default | dK/dV split |")
     w("|---|---|---|---|---|")
