@@ -65,6 +65,9 @@ step tests_fp8 300 LCA_B200_EXPERIMENTAL_FP8=1 -- python -m pytest tests/test_fp
 # 4. native dropout instantiations (coordinate-keyed keep mask regenerated in registers)
 step tests_dropout 300 LCA_B200_NATIVE_DROPOUT=1 -- python -m pytest tests/test_dropout_gpu.py -x -q -m gpu
 
+# 5. CUDA-graph capture of the single-GPU forward + backward
+step tests_graphs 240 LCA_B200_TEST_GRAPHS=1 -- python -m pytest tests/test_cuda_graph_gpu.py -x -q -m gpu
+
 grep -h '"name"' "$OUT"/perf_*.log 2>/dev/null | sed 's/^/  /' > "$OUT/summary.txt"
 for f in "$OUT"/perf_*.log; do echo "$(basename "$f" .log): $(grep -h '"name"' "$f" | python -c '
 import sys, json
