@@ -110,18 +110,33 @@ struct SchedState {
   at::Tensor counter;
   uint32_t base = 0;
 };
+// ---- build-time defaults of the opt-in kernel variants: ONE place to flip once a variant has been validated on
+// hardware (tools/validate_experimental.sh).  An environment variable, when set, always overrides the default.
+namespace defaults {
+constexpr int kF32x2 = 0;        // LCA_B200_F32X2      packed fp32x2 softmax / dS arithmetic
+constexpr int kFwdBn64 = 0;      // LCA_B200_FWD_BN64   forward with 64-row K/V tiles, double-buffered scores
+constexpr int kBwdSplit = 0;     // LCA_B200_BWD_SPLIT  backward: both warpgroups on every streamed tile
+constexpr int kDynSched = 0;     // LCA_B200_DYN_SCHED  dynamic tile scheduler (push CTAs join the compute pool)
+constexpr int kPolyEvery = 6;    // LCA_B200_POLY_EVERY exp2 offload ratio of the forward (0, 2*, 3, 4, 6; *packed variant only)
+constexpr int kNoXfix = 0;       // LCA_B200_NO_XFIX    1 = keep the pre-fix dQ-pass kernel (hang reproduction only)
+}  // namespace defaults
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
+}
+
 // packed fp32x2 element-wise arithmetic in the softmax / dS stages (EXPERIMENTAL, LCA_B200_F32X2=1)
 static int f32x2_enabled() {
-  static int e = [] { const char* v = std::getenv("LCA_B200_F32X2"); return (v && std::atoi(v) == 1) ? 1 : 0; }();
+  static int e = env_int("LCA_B200_F32X2", defaults::kF32x2) == 1 ? 1 : 0;
   return e;
 }
 // forward with 64-row K/V tiles and double-buffered scores (EXPERIMENTAL, LCA_B200_FWD_BN64=1)
 static bool bn64_enabled() {
-  static bool e = [] { const char* v = std::getenv("LCA_B200_FWD_BN64"); return v && std::atoi(v) == 1; }();
+  static bool e = env_int("LCA_B200_FWD_BN64", defaults::kFwdBn64) == 1;
   return e;
 }
 static bool dyn_sched_enabled() {
-  static bool e = [] { const char* v = std::getenv("LCA_B200_DYN_SCHED"); return v && std::atoi(v) == 1; }();
+  static bool e = env_int("LCA_B200_DYN_SCHED", defaults::kDynSched) == 1;
   return e;
 }
 template <typename P>
@@ -232,7 +247,7 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
   {
-    static int poly = [] { const char* e = std::getenv("LCA_B200_POLY_EVERY"); return e ? std::atoi(e) : 6; }();
+    static int poly = env_int("LCA_B200_POLY_EVERY", defaults::kPolyEvery);
     p.poly_every = poly;
     p.f32x2 = f32x2_enabled();
   }
@@ -585,7 +600,7 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   std::memset(&p, 0, sizeof(p));
   p.f32x2 = f32x2_enabled();
   {
-    static int sp = [] { const char* v = std::getenv("LCA_B200_BWD_SPLIT"); return (v && std::atoi(v) == 1) ? 1 : 0; }();
+    static int sp = env_int("LCA_B200_BWD_SPLIT", defaults::kBwdSplit) == 1 ? 1 : 0;
     p.split = sp;
   }
   make_tmap(&p.tm_x0, x0, "x0", 128);
@@ -658,7 +673,7 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   }
   p.out_mode = static_cast<int>(out_mode);
   // LCA_B200_NO_XFIX=1 keeps the pre-fix kernel even for launches with empty work items (only to reproduce the hang)
-  static const bool no_xfix = [] { const char* v = std::getenv("LCA_B200_NO_XFIX"); return v && std::atoi(v) == 1; }();
+  static const bool no_xfix = env_int("LCA_B200_NO_XFIX", defaults::kNoXfix) == 1;
   if (!is_dkv && !no_xfix) {
     // kXfix whenever a CTA could meet such an item right behind another work item: any empty tile (they come in long
     // runs in the collective zigzag/stripe ring), or more short items than CTAs (plain causal self-attention has one
