@@ -154,7 +154,7 @@ class FusedUSPEngine:
         """Peer slab addresses for a launch that carries push CTAs.  EXPERIMENTAL (``LCA_B200_NVLS=1`` together with
         ``LCA_B200_SLAB=vmm``): on a pure ring (U == 1) the slab's NVLS multicast address rides along as one extra
         entry and the push CTAs broadcast K/V (backward: also Q, dO, statistics) with ONE store instead of P.
-        ``LCA_B200_FAST_PUSH=1`` alone selects the same experimental push engine (16 x 16 B in flight per thread, no
+        ``LCA_B200_FAST_PUSH=1`` alone selects the same experimental push engine (8 x 16 B in flight per thread, no
         64-bit divisions) with unicast stores, on any mesh and any slab provider."""
         mc = getattr(slab, "multicast_ptr", 0)
         if mc and self.U == 1 and self.P < 16 and os.environ.get("LCA_B200_NVLS", "0") == "1":

@@ -138,3 +138,46 @@ def test_owner_computes_backward_segments_cover_every_gradient_once(U, R, varian
     for src in range(P):
         e = _engine(U, R, src % U, src // U)
         assert done_tiles[src] == U * e._bwd_segments(variant, rows)[2]
+
+
+@pytest.mark.parametrize("U,R", [(1, 2), (2, 2), (1, 8), (8, 1), (4, 2)])
+@pytest.mark.parametrize("with_bwd", [False, True])
+def test_slab_regions_are_disjoint_and_inside_the_allocation(U, R, with_bwd, monkeypatch):
+    """``FusedUSPEngine._ensure``: every staging / output tensor the forward and both backward flavours place in the
+    symmetric slab must lie inside the allocation and must not overlap a tensor that is live at the same time."""
+    import lca_b200.parallel.fused_engine as fe
+
+    class FakeSlab:
+        def __init__(self, nbytes, group, device):
+            self.nbytes = nbytes
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(fe, "_make_slab", FakeSlab)
+    for (B, rows, Hq_per_u, g, D, esz) in [(1, 8, 1, 1, 64, 2), (2, 1000, 2, 2, 128, 2), (1, 32768, 8 // min(U, 8) or 1, 1, 128, 2)]:
+        H = Hq_per_u * U * g
+        for Hkv in {H // g, max(1, U // 2)}:
+            if H % Hkv or not (Hkv % U == 0 or U % Hkv == 0):
+                continue
+            e = object.__new__(FusedUSPEngine)
+            e.U, e.R, e.P, e.u, e.r, e.me = U, R, U * R, 0, 0, 0
+            e.group, e.device, e.slab, e.key, e.with_bwd = None, None, None, None, with_bwd
+            e._ensure(B, rows, H, Hkv, D, esz)
+            P, S, Sr = U * R, U * R * rows, U * rows
+            Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
+            fwd = {"q": (e.off_q, B * Sr * Hl * D * esz), "k": (e.off_k, B * S * Hkvl * D * esz),
+                   "v": (e.off_v, B * S * Hkvl * D * esz), "o": (e.off_o, B * rows * H * D * esz),
+                   "lse_own": (e.off_lse_own, B * H * rows * 4)}
+            live_sets = [fwd]
+            if with_bwd:
+                live_sets.append({"q_all": (e.off_q, B * S * Hl * D * esz), "do_all": (e.off_do, B * S * Hl * D * esz),
+                                  "k": fwd["k"], "v": fwd["v"], "dq": fwd["o"],
+                                  "delta": (e.off_delta, B * Hl * S * 4), "lse2": (e.off_lse2, B * Hl * S * 4),
+                                  "dk": (e.off_dk, B * rows * Hkv * D * 4), "dv": (e.off_dv, B * rows * Hkv * D * 4)})
+            for regions in live_sets:
+                spans = sorted((off, off + n, name) for name, (off, n) in regions.items())
+                for (a0, a1, an), (b0, b1, bn) in zip(spans, spans[1:]):
+                    assert a1 <= b0, f"{an} [{a0},{a1}) overlaps {bn} [{b0},{b1})"
+                assert spans[-1][1] <= e.slab.nbytes
+                assert all(off % 16 == 0 for off, _, _ in spans)
