@@ -116,3 +116,29 @@ def test_exp2_polynomial_accuracy_claim():
     y = (p.view(np.int32) + (t.view(np.int32) << 23)).view(np.float32).astype(np.float64)
     ref = np.exp2(x.astype(np.float64))
     assert float(np.max(np.abs(y - ref) / ref)) < 1.1e-4
+
+
+def test_extension_entry_points_accept_the_argument_lists_python_passes():
+    """pybind arity / type check without a GPU: with CPU tensors every kernel entry point must get past argument
+    conversion (a mismatch is a TypeError) and fail later in the CUDA guard (RuntimeError)."""
+    import torch
+    if not native.extension_loaded():
+        pytest.skip("extension not built")
+    C = native.ext()._mod
+    q = torch.zeros(1, 128, 1, 128, dtype=torch.bfloat16)
+    lse, out = torch.zeros(1, 1, 128), torch.zeros_like(q)
+    qs, ks = [[0, 128, 0, -1, 0, 0, 0, 0]], [[0, 128, 0, -1, 0]]
+    xq, yk = [[0, 128, 0, 0, 0]], [[0, 128, 0, -1, 0]]
+    calls = {
+        "fmha_fwd": lambda: C.fmha_fwd(q, q, q, qs, ks, 1, 1, out, 0, lse, 0.1, -1, 0, 0.0, None, 0, 0, 0),
+        "fmha_fwd_drop": lambda: C.fmha_fwd_drop(q, q, q, qs, ks, 1, 1, out, 0, lse, 0.1, -1, 0, 0.0, None, 0, 0, 0, [26, 1, 0]),
+        "fmha_bwd_pass": lambda: C.fmha_bwd_pass(False, q, q, q, q, xq, yk, 1, 1, lse, lse, out, None, False, 0.1, -1, 0, 0.0,
+                                                 None, 0),
+        "fmha_bwd_pass_drop": lambda: C.fmha_bwd_pass_drop(False, q, q, q, q, xq, yk, 1, 1, lse, lse, out, None, False, 0.1, -1,
+                                                           0, 0.0, None, 0, [26, 1, 0]),
+    }
+    for name, fn in calls.items():
+        with pytest.raises(RuntimeError):
+            fn()
+    C.set_next_dropout([])
+    assert C.debug_count_small_tiles([[256, 0, 0]], [[256, 0, 0]], 1, 1, -1, 0) == [0, 1]
