@@ -38,7 +38,9 @@ def load(path):
 
 
 def key(name):
-    """Strip template arguments appended after validation (trailing `ELb0` flags) for matching."""
+    """Strip template arguments appended after validation (trailing `ELb0` flags) for matching, and the path-dependent
+    hash nvcc puts into the mangled name of anonymous-namespace symbols (a checkout at another path must compare equal)."""
+    name = re.sub(r"_GLOBAL__N__[0-9a-f]+_(\d+)_(\w+?)_cu_[0-9a-f]+", r"_GLOBAL__N__\1_\2_cu", name)
     return re.sub(r"(ELb0)+EEEv", "EEEv", name)
 
 
