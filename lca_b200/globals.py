@@ -92,6 +92,7 @@ def set_seq_parallel_pg(
     spec = build_mesh_spec(
         sp_ulysses_degree, sp_ring_degree, rank, world_size, use_ulysses_low
     )
+    _invalidate_fused_engines()
     PROCESS_GROUP._reset()
     PROCESS_GROUP.mesh = spec
 
@@ -121,6 +122,14 @@ def set_seq_parallel_pg(
             if rank in ranks:
                 PROCESS_GROUP.DP_PG = g
     PROCESS_GROUP.initialized = True
+
+
+def _invalidate_fused_engines() -> None:
+    """Engines of the fused NVLink backend are cached per process group; rebuilding the groups retires them."""
+    import sys
+    mod = sys.modules.get("lca_b200.parallel.fused_engine")
+    if mod is not None:
+        mod.invalidate_engines()
 
 
 def _is_self_group(group) -> bool:

@@ -23,7 +23,7 @@ from ..globals import PROCESS_GROUP, group_size
 from ..kernels import AttnType
 from ..parallel.all_to_all import SeqAllToAll4D
 from ..parallel.layout import canonical_variant
-from .attn_layer import LongContextAttention, _dropout_kw, _resolve_backend, _slice_alibi
+from .attn_layer import _dropout_kw, _resolve_backend, _slice_alibi
 from .utils import RING_IMPL_DICT
 
 
@@ -41,20 +41,16 @@ class AsyncLongContextAttention(torch.nn.Module):
         self.ring_attn_fn = RING_IMPL_DICT[ring_impl_type]
         self.attn_type = attn_type
         self.backend = _resolve_backend(backend)
-        self._fused = None
         self._comm_stream = None
-
-    _fused_engine = LongContextAttention._fused_engine
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, dropout_p=0.0, softmax_scale=None, causal=False,
                 window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False,
                 *args: Any) -> Tensor:
-        eng = None
-        if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
-            eng = self._fused_engine(query)
-        if eng is not None and eng.supports_shapes(query, key):
-            return eng.attention(query, key, value, self.variant, softmax_scale, causal, window_size, softcap,
-                                 alibi_slopes, deterministic)
+        from ..parallel.fused import try_fused
+        out = try_fused("mesh", PROCESS_GROUP, self.backend, self.attn_type, query, key, value, self.variant, dropout_p,
+                        softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic)
+        if out is not None:
+            return out
 
         U = group_size(self.ulysses_pg)
         B, Sl, H, D = query.shape

@@ -54,17 +54,6 @@ def _resolve_backend(requested: Optional[str]) -> str:
     return b
 
 
-def _fused_dropout(dropout_p, softcap):
-    """-> (fused path allowed, extra ``engine.attention`` arguments).  Dropout on the fused path needs the native
-    dropout kernels (EXPERIMENTAL, ``LCA_B200_NATIVE_DROPOUT=1``); the seed is drawn once per module call."""
-    if not dropout_p or dropout_p <= 0:
-        return True, ()
-    from ..ops import dropout as _d
-    if os.environ.get("LCA_B200_NATIVE_DROPOUT", "0") != "1" or (softcap or 0.0) != 0.0 or _d.p8_of(dropout_p) == 0:
-        return False, ()
-    return True, (float(dropout_p), int(torch.randint(1, 2**31 - 1, (1,)).item()))
-
-
 def _dropout_kw(dropout_p, ulysses_pg, local_heads: int, stage: int = 0) -> dict:
     """Extra ring-function arguments when dropout is on: one seed per module call (drawn from torch's CPU generator,
     so ranks that share ``torch.manual_seed`` share it) and the global index of this rank's first local head --
@@ -104,32 +93,15 @@ class LongContextAttention(torch.nn.Module):
         self.variant = canonical_variant(ring_impl_type)
         self.ring_attn_fn = RING_IMPL_DICT[ring_impl_type]
         self.backend = _resolve_backend(backend)
-        self._fused = None
-
-    # ------------------------------------------------------------------ fused NVLink backend
-    def _fused_engine(self, q: Tensor):
-        if self.backend == "collective":
-            return None
-        from ..parallel import fused
-
-        if self._fused is None:
-            self._fused = fused.get_engine_if_supported(PROCESS_GROUP, q, strict=self.backend == "fused")
-            if self._fused is None:
-                self._fused = False
-        return self._fused or None
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, dropout_p=0.0, softmax_scale=None, causal=False,
                 window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False,
                 *args: Any) -> Tensor:
-        eng = None
-        if not getattr(self.attn_type, "value", "").startswith("torch") and (not dropout_p or
-                                                                           os.environ.get("LCA_B200_NATIVE_DROPOUT") == "1"):
-            eng = self._fused_engine(query)
-        if eng is not None and eng.supports_shapes(query, key):
-            ok, extra = _fused_dropout(dropout_p, softcap)
-            if ok:
-                return eng.attention(query, key, value, self.variant, softmax_scale, causal, window_size, softcap,
-                                     alibi_slopes, deterministic, *extra)
+        from ..parallel.fused import try_fused
+        out = try_fused("mesh", PROCESS_GROUP, self.backend, self.attn_type, query, key, value, self.variant, dropout_p,
+                        softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic)
+        if out is not None:
+            return out
 
         alibi = _slice_alibi(alibi_slopes, self.ulysses_pg)
         if self.use_pack_qkv and key.shape == query.shape:
@@ -169,22 +141,15 @@ class LongContextAttentionQKVPacked(torch.nn.Module):
         self.variant = canonical_variant(ring_impl_type)
         self.ring_attn_fn = RING_IMPL_QKVPACKED_DICT[ring_impl_type]
         self.backend = _resolve_backend(backend)
-        self._fused = None
-
-    _fused_engine = LongContextAttention._fused_engine
 
     def forward(self, qkv: Tensor, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
                 softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False, *args: Any) -> Tensor:
-        eng = None
-        if not getattr(self.attn_type, "value", "").startswith("torch") and (not dropout_p or
-                                                                           os.environ.get("LCA_B200_NATIVE_DROPOUT") == "1"):
-            eng = self._fused_engine(qkv)
-        if eng is not None and eng.supports_shapes(qkv[:, :, 0], qkv[:, :, 1]):
-            ok, extra = _fused_dropout(dropout_p, softcap)
-            if ok:
-                # strided views of the packed tensor feed the push kernel directly: no unpack copy
-                return eng.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], self.variant, softmax_scale, causal,
-                                     window_size, softcap, alibi_slopes, deterministic, *extra)
+        from ..parallel.fused import try_fused
+        # strided views of the packed tensor feed the push kernel directly: no unpack copy
+        out = try_fused("mesh", PROCESS_GROUP, self.backend, self.attn_type, qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2],
+                        self.variant, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic)
+        if out is not None:
+            return out
         U = group_size(self.ulysses_pg)
         if U > 1:
             qkv = SeqAllToAll5D.apply(self.ulysses_pg, qkv, self.scatter_idx, self.gather_idx, self.use_sync)

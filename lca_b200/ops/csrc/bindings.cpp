@@ -113,11 +113,11 @@ struct SchedState {
 // ---- build-time defaults of the opt-in kernel variants: ONE place to flip once a variant has been validated on
 // hardware (tools/validate_experimental.sh).  An environment variable, when set, always overrides the default.
 namespace defaults {
-constexpr int kF32x2 = 0;        // LCA_B200_F32X2      packed fp32x2 softmax / dS arithmetic
-constexpr int kFwdBn64 = 0;      // LCA_B200_FWD_BN64   forward with 64-row K/V tiles, double-buffered scores
+constexpr int kF32x2 = 1;        // LCA_B200_F32X2      packed fp32x2 softmax / dS arithmetic (validated r2: bwd +4 %, D=64 fwd +22 %)
 constexpr int kBwdSplit = 0;     // LCA_B200_BWD_SPLIT  backward: both warpgroups on every streamed tile
 constexpr int kDynSched = 0;     // LCA_B200_DYN_SCHED  dynamic tile scheduler (push CTAs join the compute pool)
-constexpr int kPolyEvery = 6;    // LCA_B200_POLY_EVERY exp2 offload ratio of the forward (0, 2*, 3, 4, 6; *packed variant only)
+constexpr int kPolyEvery = 4;    // LCA_B200_POLY_EVERY exp2 offload ratio of the forward (0, 2*, 3, 4, 6; *packed variant only), head_dim 128
+constexpr int kPolyEveryD64 = 3; //                     the same for head_dim 64
 constexpr int kNoXfix = 0;       // LCA_B200_NO_XFIX    1 = keep the pre-fix dQ-pass kernel (hang reproduction only)
 }  // namespace defaults
 static int env_int(const char* name, int dflt) {
@@ -128,11 +128,6 @@ static int env_int(const char* name, int dflt) {
 // packed fp32x2 element-wise arithmetic in the softmax / dS stages (EXPERIMENTAL, LCA_B200_F32X2=1)
 static int f32x2_enabled() {
   static int e = env_int("LCA_B200_F32X2", defaults::kF32x2) == 1 ? 1 : 0;
-  return e;
-}
-// forward with 64-row K/V tiles and double-buffered scores (EXPERIMENTAL, LCA_B200_FWD_BN64=1)
-static bool bn64_enabled() {
-  static bool e = env_int("LCA_B200_FWD_BN64", defaults::kFwdBn64) == 1;
   return e;
 }
 static bool dyn_sched_enabled() {
@@ -247,8 +242,10 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
   p.flags = reinterpret_cast<const uint32_t*>(flags_ptr);
   p.flag_epoch = static_cast<uint32_t>(flag_epoch);
   {
-    static int poly = env_int("LCA_B200_POLY_EVERY", defaults::kPolyEvery);
-    p.poly_every = poly;
+    static int poly = env_int("LCA_B200_POLY_EVERY", -1);
+    // measured r2 (S=32K, packed arithmetic): D=128 is flat in the offload ratio (4: 1.971 ms, 6: 1.978 ms, 3: 2.03 ms);
+    // D=64 has twice the exponentials per tensor FLOP and wants the heavier offload (3: 3.01 ms, 6: 3.24 ms, 2: 3.83 ms)
+    p.poly_every = poly >= 0 ? poly : (D == 64 ? defaults::kPolyEveryD64 : defaults::kPolyEvery);
     p.f32x2 = f32x2_enabled();
   }
   p.lse_own_sb = out.size(2) * out.size(1);      // owners keep (B, H_total, rows) next to their (B, rows, H_total, D) output
@@ -293,13 +290,6 @@ static void fmha_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Te
   set_dropout(p, drop, softcap);
   int sms = num_sms();
   if (sm_limit > 0 && sm_limit < sms) sms = static_cast<int>(sm_limit);
-  if (bn64_enabled() && p.drop_p8 == 0) {
-    make_tmap(&p.tm_k, k, "k", 64);
-    make_tmap(&p.tm_v, v, "v", 64);
-    LCA_CUDA_OK(launch_fmha_fwd_bn64(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
-                                     at::cuda::getCurrentCUDAStream()));
-    return;
-  }
   if (p.drop_p8 == 0) attach_sched(p, q, sms, 0);     // the dropout instantiations use the static schedule
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, sms,
                               at::cuda::getCurrentCUDAStream()));
@@ -382,6 +372,17 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
   c.stage_q_rows = stage_q_rows; c.stage_kv_rows = stage_kv_rows;
   c.epoch = static_cast<unsigned int>(epoch);
   c.o_target = static_cast<unsigned int>(o_target);
+  static const int push_mode = [] {
+    const char* v = std::getenv("LCA_B200_PUSH");
+    if (!v || !*v || std::string(v) == "bulk") return 1;
+    TORCH_CHECK(std::string(v) == "scalar", "LCA_B200_PUSH must be 'bulk' or 'scalar'");
+    return 0;
+  }();
+  c.push_mode = push_mode;
+  // rows wider than one 32 KiB stage are split by the bulk engine; every size it moves is a multiple of 16 bytes
+  // because head slices are >= 128 bytes and `rows` is a multiple of 8 (FusedUSPEngine.supports_shapes)
+  static const long long wd_s = env_int("LCA_B200_WATCHDOG_S", 600);
+  c.watchdog_ns = wd_s > 0 ? static_cast<unsigned long long>(wd_s) * 1000000000ull : 0ull;
 }
 
 // EXPERIMENTAL fp8 (e4m3) forward.  q8/k8/v8: (B,S,H|Hkv,128) uint8/float8 views, scales from quantize_e4m3.
@@ -488,13 +489,6 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
   fill_comm(p.comm, mesh, ql, qo, kvl, kvo, {}, {}, false, offs[3], offs[4], peer_slabs, peer_sigs, my_sig, epoch,
             o_target, uq.size(2), uk.size(2));
   take_next_dropout(p, softcap);
-  if (bn64_enabled() && p.drop_p8 == 0 && p.comm.peer_slab[kMaxPeers - 1] == nullptr) {
-    make_tmap(&p.tm_k, k, "k", 64);
-    make_tmap(&p.tm_v, v, "v", 64);
-    LCA_CUDA_OK(launch_fmha_fwd_bn64(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
-                                     at::cuda::getCurrentCUDAStream()));
-    return;
-  }
   if (p.drop_p8 == 0) attach_sched(p, q, num_sms(), p.comm.n_comm);
   LCA_CUDA_OK(launch_fmha_fwd(p, static_cast<int>(q.size(3)), q.scalar_type() == at::kBFloat16, num_sms(),
                               at::cuda::getCurrentCUDAStream()));

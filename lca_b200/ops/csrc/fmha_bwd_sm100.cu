@@ -196,15 +196,15 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
   using C = Cfg<kD>;
   // every opt-in variant carries the x_empty fix; only the hardware-validated default keeps the old release rule
   constexpr bool kXf = (kXfix || kDyn || kPk || kDrop || kSplit || kMc) && !kIsDKV;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
-    comm_cta<kMc>(p.comm);
+    comm_role<kMc>(p.comm, smem, !kDyn);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
     // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
   }
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
 
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         if (!decode_work(p, producer_next(round), wk)) break;
         if (lane == 0) {
           const int xf = p.xseg[wk.xseg].flag;
-          if (xf >= 0 && xf != x_ok) { wait_arrival(p.flags, p.flag_epoch, xf); x_ok = xf; }
+          if (xf >= 0 && xf != x_ok) { wait_arrival(p.flags, p.flag_epoch, xf, p.comm.watchdog_ns); x_ok = xf; }
           mbar_wait(x_empty, (xc & 1) ^ 1);
           mbar_arrive_expect_tx(x_full, 2 * C::XTILE_BYTES);
 #pragma unroll
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           const uint32_t st = yc % C::STAGES;
           const uint32_t par = (yc / C::STAGES) & 1;
           if (lane == 0) {
-            if (it.flag >= 0 && it.flag != y_ok) { wait_arrival(p.flags, p.flag_epoch, it.flag); y_ok = it.flag; }
+            if (it.flag >= 0 && it.flag != y_ok) { wait_arrival(p.flags, p.flag_epoch, it.flag, p.comm.watchdog_ns); y_ok = it.flag; }
             mbar_wait(y_empty + 8 * st, par ^ 1);
             mbar_arrive_expect_tx(y_full + 8 * st, 2 * C::YTILE_BYTES);
 #pragma unroll
@@ -676,6 +676,11 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
+  if constexpr (kDyn) {
+    // the push CTAs joined the compute pool, so the "my output buffer is complete" wait moved to the end of the kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.comm.n_comm > 0 && p.comm.o_target != 0)
+      spin_until_ge(p.comm.my_sig + kSigODone, p.comm.o_target, 64, p.comm.watchdog_ns);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,9 +689,11 @@ template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDr
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
   auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit, kMc, kXfix>;
+  // fused launches: the push CTAs stage their bulk copies in the same dynamic shared memory (usp_comm.cuh)
+  constexpr int kSmem = C::SMEM_BYTES > kPushSmemBytes ? C::SMEM_BYTES : kPushSmemBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -694,7 +701,7 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
   int grid = p.total_work < avail ? p.total_work : avail;
   if (grid < 1) grid = 1;
   grid += p.comm.n_comm;       // comm CTAs first; all CTAs are co-resident (1 CTA/SM, grid <= #SMs)
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, kThreads, p.comm.n_comm > 0 ? kSmem : C::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -118,7 +118,7 @@ struct TileIter {
 };
 
 __device__ __forceinline__ void wait_flag(const FwdParams& p, int idx) {
-  wait_arrival(p.flags, p.flag_epoch, idx);
+  wait_arrival(p.flags, p.flag_epoch, idx, p.comm.watchdog_ns);
 }
 
 // four fp32 -> four e4m3 (element 0 in the lowest byte)

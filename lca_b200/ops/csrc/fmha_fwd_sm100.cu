@@ -123,7 +123,7 @@ struct TileIter {
 };
 
 __device__ __forceinline__ void wait_flag(const FwdParams& p, int idx) {
-  wait_arrival(p.flags, p.flag_epoch, idx);
+  wait_arrival(p.flags, p.flag_epoch, idx, p.comm.watchdog_ns);
 }
 
 template <bool kBf16>
@@ -158,15 +158,15 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
   // never complete two phases under the MMA warp's parity wait (docs/ROUND2_PLAN.md, "Robustness item"); the
   // hardware-validated default keeps its original rule (the warpgroup waits q_full itself)
   constexpr bool kQf = kDyn || kPk || kDrop || kMc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
-    comm_cta<kMc>(p.comm);
+    comm_role<kMc>(p.comm, smem, !kDyn);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
     // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
   }
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
 
@@ -683,6 +683,11 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
+  if constexpr (kDyn) {
+    // the push CTAs joined the compute pool, so the "my output buffer is complete" wait moved to the end of the kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.comm.n_comm > 0 && p.comm.o_target != 0)
+      spin_until_ge(p.comm.my_sig + kSigODone, p.comm.o_target, 64, p.comm.watchdog_ns);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -692,9 +697,11 @@ template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false, bool kDrop
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
   auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk, kDrop, kMc>;
+  // fused launches: the push CTAs stage their bulk copies in the same dynamic shared memory (usp_comm.cuh)
+  constexpr int kSmem = C::SMEM_BYTES > kPushSmemBytes ? C::SMEM_BYTES : kPushSmemBytes;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -702,7 +709,7 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
   int grid = p.total_work < avail ? p.total_work : avail;
   if (grid < 1) grid = 1;
   grid += p.comm.n_comm;       // comm CTAs first; all CTAs are co-resident (1 CTA/SM, grid <= #SMs)
-  kern<<<grid, kThreads, C::SMEM_BYTES, stream>>>(p);
+  kern<<<grid, kThreads, p.comm.n_comm > 0 ? kSmem : C::SMEM_BYTES, stream>>>(p);
   return cudaGetLastError();
 }
 

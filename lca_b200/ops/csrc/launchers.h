@@ -11,8 +11,6 @@ namespace lca {
 // fmha_fwd_sm100.cu
 cudaError_t launch_fmha_fwd(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream);
 
-// fmha_fwd_bn64_sm100.cu (experimental: 64-row K/V tiles, double-buffered scores; tm_k / tm_v need 64-row boxes)
-cudaError_t launch_fmha_fwd_bn64(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream);
 
 // fmha_fwd_fp8_sm100.cu (experimental)
 cudaError_t launch_fmha_fwd_fp8(const FwdParams& p, int head_dim, int num_sms, cudaStream_t stream);

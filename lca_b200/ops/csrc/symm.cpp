@@ -27,7 +27,11 @@ namespace lca {
 static int64_t symm_alloc(int64_t bytes, int64_t device) {
   c10::cuda::CUDAGuard guard(static_cast<c10::DeviceIndex>(device));
   void* p = nullptr;
-  SYMM_OK(cudaMalloc(&p, static_cast<size_t>(bytes)));
+  const cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();      // out-of-memory is not sticky: clear it so the caller can fall back
+    TORCH_CHECK(false, "symm_alloc: cudaMalloc(", bytes, " bytes) failed: ", cudaGetErrorString(e));
+  }
   SYMM_OK(cudaMemset(p, 0, static_cast<size_t>(bytes)));
   SYMM_OK(cudaDeviceSynchronize());
   return reinterpret_cast<int64_t>(p);

@@ -208,10 +208,10 @@ def fmha_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p, out=None, lse=None, sm_
 
 
 def dropout_supported(p) -> bool:
-    """EXPERIMENTAL (``LCA_B200_NATIVE_DROPOUT=1``): the ``kDrop`` kernel instantiations regenerate the coordinate-keyed
-    keep mask of ``ops/dropout.py`` in registers.  Not yet validated on hardware, hence opt-in; softcap + dropout stays
-    on the PyTorch engine."""
-    return (os.environ.get("LCA_B200_NATIVE_DROPOUT", "0") == "1" and float(getattr(p, "softcap", 0.0)) == 0.0
+    """The ``kDrop`` kernel instantiations regenerate the coordinate-keyed keep mask of ``ops/dropout.py`` in registers.
+    Default since round 2 (validated on hardware against the PyTorch engine, ``tests/test_dropout_gpu.py``;
+    ``LCA_B200_NATIVE_DROPOUT=0`` opts out); softcap + dropout stays on the PyTorch engine."""
+    return (os.environ.get("LCA_B200_NATIVE_DROPOUT", "1") == "1" and float(getattr(p, "softcap", 0.0)) == 0.0
             and _dropout.p8_of(p.dropout_p) > 0)
 
 

@@ -1,5 +1,33 @@
-"""Fused NVLink backend entry points (engine lives in fused_engine.py once symmetric memory is up)."""
+"""Entry point of the fused NVLink backend shared by ``LongContextAttention``, ``LongContextAttentionQKVPacked`` and
+``UlyssesAttention``: decides PER CALL whether the fused engine can take the inputs (the engine object itself is cached
+per process group in :mod:`fused_engine`; nothing about one call's dtype / head_dim is remembered for the next),
+reserves the symmetric slab (falling back consistently across ranks when it does not fit), agrees on the dropout seed,
+and wraps the launch in an NVTX range."""
 from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from ..utils.logging import get_logger
+from ..utils.profiling import nvtx_range
+
+_LOG = get_logger()
+_REPORTED = set()
+
+
+def _note_once(key, msg: str, level: str = "info") -> None:
+    """Fallback decisions are logged once per distinct reason (LCA_B200_LOGLEVEL=INFO shows them)."""
+    if key not in _REPORTED:
+        _REPORTED.add(key)
+        getattr(_LOG, level)(msg)
+
+
+def native_dropout_enabled() -> bool:
+    """In-kernel dropout (coordinate-keyed masks, validated on hardware in round 2) is the default;
+    ``LCA_B200_NATIVE_DROPOUT=0`` restores the PyTorch engine for ``dropout_p > 0``."""
+    return os.environ.get("LCA_B200_NATIVE_DROPOUT", "1") == "1"
 
 
 def get_engine_if_supported(process_group_state, q, strict: bool = False):
@@ -20,3 +48,40 @@ def get_ulysses_engine_if_supported(group, q, strict: bool = False):
             raise
         return None
     return engine_for_ulysses_group(group, q, strict)
+
+
+def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dropout_p, softmax_scale, causal,
+              window_size, softcap, alibi_slopes, deterministic) -> Optional[torch.Tensor]:
+    """Run one attention call on the fused engine.  ``kind``: "mesh" (``pg`` = PROCESS_GROUP state) or "ulysses"
+    (``pg`` = the sequence process group).  Returns ``None`` when the caller has to take the collective path."""
+    if backend == "collective" or getattr(attn_type, "value", "").startswith("torch"):
+        return None
+    strict = backend == "fused"
+    dropout_p = float(dropout_p or 0.0)
+    if dropout_p > 0.0:
+        from ..ops import dropout as _d
+        if not native_dropout_enabled() or float(softcap or 0.0) != 0.0:
+            _note_once(("dropout", kind), "fused backend skipped: dropout with softcap / LCA_B200_NATIVE_DROPOUT=0")
+            return None
+        if _d.p8_of(dropout_p) == 0:
+            dropout_p = 0.0
+    eng = get_engine_if_supported(pg, q, strict) if kind == "mesh" else get_ulysses_engine_if_supported(pg, q, strict)
+    if eng is None:
+        return None
+    if not eng.supports_shapes(q, k):
+        if strict:
+            raise RuntimeError(f"fused backend cannot take q {tuple(q.shape)} / k {tuple(k.shape)} on a "
+                               f"{eng.U}x{eng.R} mesh (rows % 8, head divisibility)")
+        _note_once(("shape", tuple(q.shape), tuple(k.shape)), f"fused backend skipped for q {tuple(q.shape)} k {tuple(k.shape)}")
+        return None
+    need_bwd = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+    if not eng.reserve(q, k, need_bwd):
+        if strict:
+            raise RuntimeError("fused backend: the symmetric slab does not fit (LCA_B200_SLAB_MAX_GB / free memory)")
+        _note_once(("slab", tuple(q.shape)), f"fused backend skipped: staging slab for q {tuple(q.shape)} does not fit; "
+                   "using the collective path", "warning")
+        return None
+    seed = eng.dropout_seed() if dropout_p > 0.0 else 0
+    with nvtx_range(f"lca.fused.{kind}.{variant}"):
+        return eng.attention(q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
+                             dropout_p, seed)

@@ -39,7 +39,11 @@ import torch.distributed as dist
 
 from ..ops import native
 from ..ops.attention import AttnParams
+from ..utils.logging import get_logger
+from ..utils.profiling import nvtx_range
 from .layout import Seg, canonical_variant, ring_positions
+
+_LOG = get_logger()
 
 SIG_BYTES = 4096
 SIG_KV, SIG_Q, SIG_RTR, SIG_ODONE, SIG_DKV, SIG_QA = 0, 16, 32, 48, 49, 64
@@ -51,55 +55,63 @@ def _align(x: int) -> int:
     return (x + _ALIGN - 1) // _ALIGN * _ALIGN
 
 
-class _Slab:
-    """This rank's symmetric slab + mapped views of every peer's slab."""
+class _SlabDoesNotFit(RuntimeError):
+    pass
 
-    def __init__(self, nbytes: int, group, device: torch.device):
+
+class _Slab:
+    """This rank's symmetric slab + mapped views of every peer's slab (cudaMalloc + legacy CUDA IPC)."""
+
+    def __init__(self, nbytes: int, device: torch.device):
         C = native.ext()
         self.nbytes = nbytes
         self.device = device
-        self.ptr = C.symm_alloc(nbytes, device.index)
+        self.ptr = C.symm_alloc(nbytes, device.index)       # raises on out-of-memory
+        self.peer_ptrs = None
+        self._me = -1
+
+    def exchange(self, group):
+        C = native.ext()
         handle = C.symm_export(self.ptr)
         world = dist.get_world_size(group)
         handles: List[Optional[bytes]] = [None] * world
         dist.all_gather_object(handles, handle, group=group)
         me = dist.get_rank(group)
-        self.peer_ptrs = [self.ptr if i == me else C.symm_import(handles[i], device.index) for i in range(world)]
+        self.peer_ptrs = [self.ptr if i == me else C.symm_import(handles[i], self.device.index) for i in range(world)]
         self._me = me
+        return self
 
     def tensor(self, offset: int, shape, dtype) -> torch.Tensor:
         return native.ext().symm_tensor(self.ptr + offset, list(shape), dtype, self.device.index)
 
+    def free_local(self):
+        native.ext().symm_free(self.ptr)
+
     def close(self):
         C = native.ext()
-        for i, p in enumerate(self.peer_ptrs):
+        for i, p in enumerate(self.peer_ptrs or []):
             if i != self._me:
                 C.symm_unmap(p)
         C.symm_free(self.ptr)
 
 
 class _VmmSlab:
-    """Opt-in slab provider (``LCA_B200_SLAB=vmm``): ``torch.distributed._symmetric_memory``.
+    """Opt-in slab provider (``LCA_B200_SLAB=vmm``): ``torch.distributed._symmetric_memory`` (CUDA VMM API:
+    ``cuMemCreate`` / ``cuMemMap`` / ``cuMemSetAccess``; only the slab itself is peer-visible, and the NVLS multicast
+    address is available for the broadcast push).  Same interface as ``_Slab``; allocation and rendezvous are one
+    collective step."""
 
-    The default ``_Slab`` shares a ``cudaMalloc`` allocation through legacy CUDA IPC, which turns on device-wide
-    peer access: from then on every *later* ``cudaMalloc`` of a rank has to be mapped into its peers' contexts,
-    and that mapping can wait for a peer's running kernel.  A persistent kernel that spins on a flag of a rank
-    whose host is inside ``cudaMalloc`` would then never be released (suspected cause of the one hang seen in
-    round 1: fused forward + NCCL backward at N=4, where NCCL's lazy communicator creation de-synchronises
-    the hosts while the caching allocator is still growing).  The torch provider allocates with the CUDA VMM API
-    (``cuMemCreate`` / ``cuMemMap`` / ``cuMemSetAccess``): only the slab itself is peer-visible, ordinary
-    allocations never touch a peer.  It also exposes the NVLS multicast address (``multicast_ptr``) that the
-    round-2 K/V broadcast wants.  Same interface as ``_Slab``.  Not yet exercised on hardware.
-    """
-
-    def __init__(self, nbytes: int, group, device: torch.device):
+    def __init__(self, nbytes: int, device: torch.device):
         import torch.distributed._symmetric_memory as symm
         self.nbytes = nbytes
         self.device = device
-        pg = group if group is not None else dist.group.WORLD
         self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
         self.buf.zero_()
         torch.cuda.synchronize(device)
+
+    def exchange(self, group):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
         self.hdl = symm.rendezvous(self.buf, pg)          # collective: also orders the zero-fill before any push
         self.ptr = int(self.buf.data_ptr())
         self.peer_ptrs = [int(x) for x in self.hdl.buffer_ptrs]
@@ -111,6 +123,7 @@ class _VmmSlab:
         except Exception:   # noqa: BLE001 - no NVLS on this box / build
             self.multicast_ptr = 0
         dist.barrier(group=pg)
+        return self
 
     def tensor(self, offset: int, shape, dtype) -> torch.Tensor:
         n = 1
@@ -119,18 +132,25 @@ class _VmmSlab:
         nb = n * torch.empty((), dtype=dtype).element_size()
         return self.buf[offset:offset + nb].view(dtype).view(*shape)
 
+    def free_local(self):
+        self.buf = None
+
     def close(self):
         self.hdl = None
         self.buf = None
 
 
-def _make_slab(nbytes: int, group, device: torch.device):
+def _make_slab_local(nbytes: int, device: torch.device):
     kind = os.environ.get("LCA_B200_SLAB", "ipc")
     if kind == "vmm":
-        return _VmmSlab(nbytes, group, device)
+        return _VmmSlab(nbytes, device)
     if kind != "ipc":
         raise ValueError(f"LCA_B200_SLAB={kind!r}: expected 'ipc' or 'vmm'")
-    return _Slab(nbytes, group, device)
+    return _Slab(nbytes, device)
+
+
+def _make_slab(nbytes: int, group, device: torch.device):
+    return _make_slab_local(nbytes, device).exchange(group)
 
 
 class FusedUSPEngine:
@@ -146,6 +166,8 @@ class FusedUSPEngine:
         self.o_total = 0
         self.dkv_total = 0
         self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "8"))
+        self._refused = set()                   # call shapes whose slab did not fit (decided collectively, once)
+        self.slab_bytes = 0
         self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
         self.sig = _make_slab(SIG_BYTES, sp_group, device)
@@ -163,6 +185,19 @@ class FusedUSPEngine:
             return list(slab.peer_ptrs) + [1]        # sentinel: experimental push engine, unicast only
         return slab.peer_ptrs
 
+    def close(self) -> None:
+        """Release the slabs (collective: peers must have stopped writing)."""
+        torch.cuda.synchronize(self.device)
+        try:
+            dist.barrier(group=self.group)
+        except Exception:   # noqa: BLE001 - the group may already be gone at interpreter exit
+            pass
+        for sl in (self.slab, self.sig):
+            if sl is not None:
+                sl.close()
+        self.slab = self.sig = None
+        self.key = None
+
     def supports_shapes(self, q, k) -> bool:
         """Shapes the push CTAs / kernels can handle; anything else takes the collective path."""
         rows, H, Hkv = q.shape[1], q.shape[2], k.shape[2]
@@ -170,39 +205,111 @@ class FusedUSPEngine:
                 and (Hkv % self.U == 0 or self.U % Hkv == 0) and H % Hkv == 0)
 
     # ------------------------------------------------------------------------------ workspace
-    def _ensure(self, B, rows, H, Hkv, D, esz):
-        U, R = self.U, self.R
+    def _layout(self, B, rows, H, Hkv, D, esz, bwd: bool):
+        """Byte offsets of the staging tensors inside the slab -> (offsets dict, total bytes).  Forward-only calls
+        (``torch.no_grad`` / inference) stage K/V of the whole sequence and Q of my ring block only; the
+        owner-computes backward additionally stages Q, dO and the row statistics of every rank."""
+        U = self.U
         Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
-        key = (B, rows, H, Hkv, D, esz)
-        if key == self.key:
-            return
         S = self.P * rows
-        sq = B * (S if self.with_bwd else U * rows) * Hl * D * esz          # fwd: my ring block; bwd: every token
+        sq = B * (S if bwd else U * rows) * Hl * D * esz          # fwd: my ring block; bwd: every token
         skv = B * S * Hkvl * D * esz
         so = B * rows * H * D * esz
         sstat = B * Hl * S * 4
         sdkv = B * rows * Hkv * D * 4
-        self.off_q = 0
-        self.off_k = _align(self.off_q + sq)
-        self.off_v = _align(self.off_k + skv)
-        self.off_o = _align(self.off_v + skv)                  # out (fwd) / dq (bwd)
-        self.off_lse_own = _align(self.off_o + so)              # (B, H, rows) fp32 LSE of my tokens (written by compute ranks)
-        self.off_do = _align(self.off_lse_own + B * H * rows * 4)
-        self.off_delta = _align(self.off_do + (sq if self.with_bwd else 0))
-        self.off_lse2 = _align(self.off_delta + (sstat if self.with_bwd else 0))
-        self.off_dk = _align(self.off_lse2 + (sstat if self.with_bwd else 0))
-        self.off_dv = _align(self.off_dk + (sdkv if self.with_bwd else 0))
-        total = _align(self.off_dv + (sdkv if self.with_bwd else 0)) + _ALIGN
+        o = {}
+        o["q"] = 0
+        o["k"] = _align(o["q"] + sq)
+        o["v"] = _align(o["k"] + skv)
+        o["o"] = _align(o["v"] + skv)                    # out (fwd) / dq (bwd)
+        o["lse_own"] = _align(o["o"] + so)               # (B, H, rows) fp32 LSE of my tokens (written by compute ranks)
+        o["do"] = _align(o["lse_own"] + B * H * rows * 4)
+        o["delta"] = _align(o["do"] + (sq if bwd else 0))
+        o["lse2"] = _align(o["delta"] + (sstat if bwd else 0))
+        o["dk"] = _align(o["lse2"] + (sstat if bwd else 0))
+        o["dv"] = _align(o["dk"] + (sdkv if bwd else 0))
+        total = _align(o["dv"] + (sdkv if bwd else 0)) + _ALIGN
+        return o, total
+
+    def staging_bytes(self, B, rows, H, Hkv, D, esz, bwd: bool) -> int:
+        return self._layout(B, rows, H, Hkv, D, esz, bwd)[1]
+
+    def _agree(self, ok: bool) -> bool:
+        """Logical AND of ``ok`` over the sp group (every rank must take the same backend)."""
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def reserve(self, q, k, need_bwd: bool) -> bool:
+        """Make sure the slab can hold this call (collective only when it has to grow).  Returns False -- on EVERY
+        rank -- when the slab would exceed ``LCA_B200_SLAB_MAX_GB`` (default: 60 % of the memory that is free right
+        now) or cannot be allocated; the caller then uses the collective backend, whose memory is O(S/P)."""
+        B, rows, H, D = q.shape
+        bwd = bool(need_bwd and self.with_bwd)
+        key = (B, rows, H, k.shape[2], D, q.element_size(), bwd)
+        if key == self.key:
+            return True
+        if key in self._refused:
+            return False
+        try:
+            self._ensure(*key)
+            return True
+        except _SlabDoesNotFit:
+            self._refused.add(key)
+            return False
+
+    def _ensure(self, B, rows, H, Hkv, D, esz, bwd: bool = True):
+        key = (B, rows, H, Hkv, D, esz, bwd)
+        if key == self.key:
+            return
+        offs, total = self._layout(B, rows, H, Hkv, D, esz, bwd)
         if self.slab is None or self.slab.nbytes < total:
+            have = self.slab.nbytes if self.slab is not None else 0
+            cap_gb = float(os.environ.get("LCA_B200_SLAB_MAX_GB", "0") or 0)
+            free = torch.cuda.mem_get_info(self.device)[0] + have
+            cap = int(cap_gb * 2**30) if cap_gb > 0 else int(0.6 * free)
+            if not self._agree(total <= cap):
+                raise _SlabDoesNotFit(f"slab of {total / 2**30:.2f} GiB exceeds the cap ({cap / 2**30:.2f} GiB)")
             if self.slab is not None:
                 torch.cuda.synchronize(self.device)
                 dist.barrier(group=self.group)      # nobody may still be writing into the old slab
                 self.slab.close()
-            self.slab = _make_slab(total, self.group, self.device)
+                self.slab = None
+            new = None
+            try:
+                new = _make_slab_local(total, self.device)
+            except RuntimeError:
+                torch.cuda.empty_cache()            # the caching allocator may be sitting on the memory we need
+                try:
+                    new = _make_slab_local(total, self.device)
+                except RuntimeError:
+                    new = None
+            if not self._agree(new is not None):
+                if new is not None:
+                    new.free_local()
+                raise _SlabDoesNotFit(f"could not allocate a {total / 2**30:.2f} GiB symmetric slab on every rank")
+            self.slab = new.exchange(self.group)
+            _LOG.info("fused engine %dx%d: slab %.2f GiB (%s)", self.U, self.R, total / 2**30,
+                      "fwd+bwd staging" if bwd else "fwd staging")
+        self.off_q, self.off_k, self.off_v, self.off_o = offs["q"], offs["k"], offs["v"], offs["o"]
+        self.off_lse_own, self.off_do, self.off_delta = offs["lse_own"], offs["do"], offs["delta"]
+        self.off_lse2, self.off_dk, self.off_dv = offs["lse2"], offs["dk"], offs["dv"]
         self.key = key
+        self.slab_bytes = self.slab.nbytes
+
+    def dropout_seed(self) -> int:
+        """One seed per module call, identical on every sp rank whatever their ``torch.manual_seed``: the first rank of
+        the group draws it from torch's CPU generator (so a seeded run is reproducible and matches a single-device run
+        with the same seed) and broadcasts it.  The owner-computes backward regenerates masks of queries whose forward
+        ran on another rank -- with per-rank seeds dK/dV would silently be wrong."""
+        seed = torch.randint(1, 2**31 - 1, (1,), dtype=torch.int64)
+        t = seed.to(self.device)
+        g = self.group if self.group is not None else dist.group.WORLD
+        dist.broadcast(t, src=dist.get_global_rank(g, 0), group=g)
+        return int(t.item())
 
     # ------------------------------------------------------------------------------ forward
-    def forward(self, q, k, v, variant: str, p: AttnParams):
+    def forward(self, q, k, v, variant: str, p: AttnParams, need_bwd: bool = True):
         """q (B, S/P, H, D), k/v (B, S/P, Hkv, D) local shards -> out (B, S/P, H, D), lse (B, H/U, S/R)."""
         C = native.ext()
         U, R, u, r, P = self.U, self.R, self.u, self.r, self.P
@@ -215,7 +322,7 @@ class FusedUSPEngine:
             raise ValueError(f"kv heads ({Hkv}) must divide or be divisible by the Ulysses degree ({U})")
         Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
         q, k, v = (_dense_heads(t) for t in (q, k, v))
-        self._ensure(B, rows, H, Hkv, D, esz)
+        self._ensure(B, rows, H, Hkv, D, esz, bool(need_bwd and self.with_bwd))
         slab = self.slab
         Sr = U * rows                            # tokens per ring rank after the Ulysses gather
         self.epoch += 1
@@ -335,7 +442,7 @@ class FusedUSPEngine:
         esz = q.element_size()
         Hl, Hkvl = H // U, Hkv // U
         q, k, v, dout = (_dense_heads(t) for t in (q, k, v, dout))
-        self._ensure(B, rows, H, Hkv, D, esz)
+        self._ensure(B, rows, H, Hkv, D, esz, True)
         slab = self.slab
         Sr, S = U * rows, P * rows
         delta_local = native.attn_delta(out, dout)                                   # (B, H, rows)
@@ -390,7 +497,7 @@ class FusedUSPEngine:
         esz = q.element_size()
         Hl, Hkvl = H // U, (Hkv // U if Hkv >= U else 1)
         q, k, v, dout = (_dense_heads(t) for t in (q, k, v, dout))
-        self._ensure(B, rows, H, Hkv, D, esz)
+        self._ensure(B, rows, H, Hkv, D, esz, True)
         slab = self.slab
         Sr = U * rows
         pushed = U > 1
@@ -495,7 +602,7 @@ _SelfGroup = _SelfGroupType()
 class _FusedAttnFunc(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams):
-        out, lse, lse_own = eng.forward(q, k, v, variant, p)
+        out, lse, lse_own = eng.forward(q, k, v, variant, p, need_bwd=any(ctx.needs_input_grad[:3]))
         ctx.save_for_backward(q, k, v, out, lse, lse_own)
         ctx.eng, ctx.variant, ctx.p = eng, variant, p
         return out
@@ -529,6 +636,15 @@ class _FusedAttnFunc(torch.autograd.Function):
 
 # ---------------------------------------------------------------------------------- factories
 _ENGINES = {}
+
+
+def invalidate_engines() -> None:
+    """Drop every cached engine (called by ``set_seq_parallel_pg``: the process groups the engines were built on are
+    being replaced, and ``id(group)`` of a new group may collide with a dead one).  Collective over each engine's group."""
+    for key, eng in list(_ENGINES.items()):
+        if eng is not None:
+            eng.close()
+    _ENGINES.clear()
 
 
 def _same_node_p2p(group, device) -> bool:

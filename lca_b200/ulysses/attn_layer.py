@@ -29,26 +29,15 @@ class UlyssesAttention(torch.nn.Module):
         self.attn_type = attn_type
         self.attn_fn = select_flash_attn_impl(attn_type, stage="fwd-bwd")
         self.backend = _resolve_backend(backend)
-        self._fused = None
-
-    def _fused_engine(self, q: Tensor):
-        if self.backend == "collective":
-            return None
-        from ..parallel import fused
-
-        if self._fused is None:
-            self._fused = fused.get_ulysses_engine_if_supported(self.spg, q, strict=self.backend == "fused") or False
-        return self._fused or None
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor, dropout_p=0.0, softmax_scale=None, causal=False,
                 window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False,
                 *args: Any) -> Tensor:
-        eng = None
-        if dropout_p == 0.0 and not getattr(self.attn_type, "value", "").startswith("torch"):
-            eng = self._fused_engine(query)
-        if eng is not None and eng.supports_shapes(query, key):
-            return eng.attention(query, key, value, "basic", softmax_scale, causal, window_size, softcap,
-                                 alibi_slopes, deterministic)
+        from ..parallel.fused import try_fused
+        out = try_fused("ulysses", self.spg, self.backend, self.attn_type, query, key, value, "basic", dropout_p,
+                        softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic)
+        if out is not None:
+            return out
         q = SeqAllToAll4D.apply(self.spg, query, self.scatter_idx, self.gather_idx, self.use_sync)
         k = SeqAllToAll4D.apply(self.spg, key, self.scatter_idx, self.gather_idx, self.use_sync)
         v = SeqAllToAll4D.apply(self.spg, value, self.scatter_idx, self.gather_idx, self.use_sync)

@@ -6,7 +6,7 @@ and the opt-in ``kSplit`` variant (both warpgroups work on every tile, 32 column
 Role threads (producer warp, MMA issuer, two element-wise warpgroups) run the kernel's control flow against modelled
 mbarriers and an in-order asynchronous tensor pipe; every buffer (X tile, Y ring, statistics ring, the two T/dS TMEM
 stages, the accumulators) carries a state machine, so a protocol error is an assertion and a missed phase a timeout.
-Same construction as ``test_bn64_pipeline_model_cpu.py``."""
+Modelled mbarriers: ``pipeline_model.py``."""
 import queue
 import random
 import threading
@@ -14,7 +14,7 @@ import time
 
 import pytest
 
-from test_bn64_pipeline_model_cpu import MBar
+from pipeline_model import MBar
 
 STAGES = 4
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LCA_B200_NATIVE_DROPOUT", "0") != "1",
+              pytest.mark.skipif(os.environ.get("LCA_B200_NATIVE_DROPOUT", "1") != "1",
                                  reason="native dropout kernels are opt-in until validated on hardware")]
 
 CASES = [

@@ -1,6 +1,6 @@
 """Executable model of the barrier protocol of ``csrc/fmha_fwd_sm100.cu`` (one 128-column score buffer per Q tile,
 tensor-pipe order ``QK0(j+1) | PV1(j) | QK1(j+1) | PV0(j+1)``, 5-slot K/V ring), in the form the opt-in variants use
-(``kQf``: empty work items are handed back through ``o_full``).  Same construction as the BN64 and backward models."""
+(``kQf``: empty work items are handed back through ``o_full``).  Same construction as the backward model."""
 import queue
 import random
 import threading
@@ -8,7 +8,7 @@ import time
 
 import pytest
 
-from test_bn64_pipeline_model_cpu import MBar
+from pipeline_model import MBar
 
 STAGES = 5
 
