@@ -50,7 +50,24 @@ def parse():
                     help="cpu = control-flow dry run for the CPU test-suite (gloo, PyTorch engine, host timers); "
                          "numbers from it are meaningless")
     ap.add_argument("--qkvpacked", action="store_true", help="LongContextAttentionQKVPacked (BASELINE config 5; MHA only)")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE.json config preset (2: pure Ulysses S=32K h=32; 3: pure ring zigzag S=256K h=8 [the default]; "
+                         "4: U=2 x ring zigzag GQA kv=4 S=128K window; 5: U=4 x ring qkvpacked S=64K h=16); explicit flags win")
+    ap.add_argument("--fp8", action="store_true", help="ours: e4m3 block-scaled forward (config 5); backward stays bf16")
+    ap.add_argument("--no-check", action="store_true", help="skip the fp32 sampled-row correctness check after the timed regions")
+    a = ap.parse_args()
+    presets = {
+        2: dict(seq=32 * 1024, heads=32, ulysses=8, ring_impl="basic"),
+        3: dict(seq=256 * 1024, heads=8, ulysses=1, ring_impl="zigzag"),
+        4: dict(seq=128 * 1024, heads=32, kv_heads=4, ulysses=2, ring_impl="zigzag", window=8192),
+        5: dict(seq=64 * 1024, heads=16, ulysses=4, ring_impl="zigzag", qkvpacked=True),
+    }
+    if a.config:
+        given = {x.split("=")[0].lstrip("-").replace("-", "_") for x in sys.argv[1:] if x.startswith("--")}
+        for key, val in presets[a.config].items():
+            if key not in given:
+                setattr(a, key, val)
+    return a
 
 
 class ClockSampler:
@@ -358,6 +375,78 @@ def main():
             comm_probe = {"compute_only_ms": round(float(t[0]), 4), "exposed_comm_ms": round(ms - float(t[0]), 4),
                           "how": "same kernels, same per-rank problem, all operands local (no NVLink); max over ranks"}
 
+    # ------------------------------------------------------------------ correctness (outside every timer)
+    # One more step on the device-resident shards; the last kv head (and its query heads) of out / dq / dk / dv is
+    # gathered into natural token order and compared on sampled rows / columns with the chunked fp32 oracle
+    # (lca_b200/ops/sampled_oracle.py) evaluated on the gathered K/V.  Every rank checks its own sample.
+    check = None
+    if not a.no_check and not on_cpu:
+        try:
+            from lca_b200.ops.sampled_oracle import head_oracle, rel_err
+            from lca_b200.parallel.layout import canonical_variant, gather_global
+            variant = canonical_variant(a.ring_impl)
+            qc, kc, vc = (t.detach().clone().requires_grad_(need_grad) for t in (q, k, v))
+            oc = call(qc, kc, vc) if need_grad else step(qc, kc, vc)
+            if need_grad:
+                oc.backward(dout)
+            G, hk = H // Hkv, Hkv - 1
+
+            def glob(t):
+                t = t.detach().contiguous()
+                if world == 1:
+                    return t
+                parts = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(parts, t)
+                return gather_global(variant, parts, R, U)
+
+            hs = slice(hk * G, (hk + 1) * G)
+            gq, gk, gv, go = glob(q[:, :, hs]), glob(k[:, :, hk:hk + 1]), glob(v[:, :, hk:hk + 1]), glob(oc[:, :, hs])
+            gdo = glob(dout[:, :, hs]) if need_grad else None
+            gs = torch.Generator().manual_seed(4321 + rank)
+            n_rows, n_cols = 128, (64 if need_grad else 0)
+            rows = torch.randint(0, S, (n_rows,), generator=gs)
+            rows[0], rows[1] = 0, S - 1
+            cols = None
+            if n_cols:
+                cols = torch.randint(0, S, (n_cols,), generator=gs)
+                cols[0], cols[1] = 0, S - 1
+            win = (a.window, 0 if causal else a.window) if a.window >= 0 else (-1, -1)
+            ref = head_oracle(gq[0], gk[0, :, 0], gv[0, :, 0], gdo[0] if need_grad else None, rows, cols, causal=causal,
+                              window=win, chunk=2048)
+            rows_d = rows.to(dev)
+            errs = {"max_err_out": float((go[0, rows_d].float() - ref["out"]).abs().max())}
+            if need_grad:
+                cols_d = cols.to(dev)
+                errs["max_rel_err_dq"] = rel_err(glob(qc.grad[:, :, hs])[0, rows_d], ref["dq"])
+                errs["max_rel_err_dk"] = rel_err(glob(kc.grad[:, :, hk:hk + 1])[0, cols_d, 0], ref["dk"])
+                errs["max_rel_err_dv"] = rel_err(glob(vc.grad[:, :, hk:hk + 1])[0, cols_d, 0], ref["dv"])
+            t = torch.tensor([errs.get("max_err_out", 0.0), errs.get("max_rel_err_dq", 0.0), errs.get("max_rel_err_dk", 0.0),
+                              errs.get("max_rel_err_dv", 0.0)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            vals = [float(x) for x in t]
+            ok = vals[0] < 2e-2 and all(x < 3e-2 for x in vals[1:]) and all(x == x for x in vals)
+            check = {"max_err_out": round(vals[0], 5), "ok": bool(ok), "rows_per_rank": n_rows, "cols_per_rank": n_cols,
+                     "head": int(hk), "oracle": "fp32 chunked softmax on gathered K/V (ops/sampled_oracle.py)"}
+            if need_grad:
+                check.update({"max_rel_err_dq": round(vals[1], 5), "max_rel_err_dk": round(vals[2], 5),
+                              "max_rel_err_dv": round(vals[3], 5)})
+            if a.window >= 0 and a.impl == "reference":
+                check["note"] = "the reference applies the window per ring block without global offsets (BASELINE.md section 7)"
+            del gq, gk, gv, go, gdo, ref
+        except Exception as e:  # noqa: BLE001
+            check = {"ok": False, "error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+    staging = None
+    if a.impl == "ours" and world > 1:
+        try:
+            from lca_b200.parallel import fused_engine as _fe
+            engs = [e for e in _fe._ENGINES.values() if e is not None]
+            if engs:
+                staging = {"slab_bytes_per_rank": int(engs[0].slab_bytes), "push_ctas": int(engs[0].n_comm)}
+        except Exception:  # noqa: BLE001
+            pass
+
     flops = 4.0 * B * H * S * S * D * (0.5 if causal else 1.0)
     if need_grad:
         flops *= 3.5
@@ -381,9 +470,13 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(n_launch * a.steps) if a.impl == "ours" else None,
             "comm": comm_probe,
+            "check": check,
+            "staging": staging,
         }))
     if need_dist:
         dist.destroy_process_group()
+    if a.impl == "ours" and check is not None and not check.get("ok", False):
+        raise SystemExit(3)          # a wrong answer must not look like a benchmark result
 
 
 if __name__ == "__main__":

@@ -108,7 +108,7 @@ class AsyncLongContextAttention(torch.nn.Module):
                                    window_size=window_size, softcap=softcap,
                                    alibi_slopes=None if alibi is None else alibi[..., i:i + 1].contiguous(),
                                    deterministic=deterministic, return_attn_probs=False, group=self.ring_pg,
-                                   attn_type=self.attn_type,
+                                   attn_type=self.attn_type, backend="collective",
                                    **(dict(dkw, head_offset=dkw["head_offset"] + i) if dkw else {}))
             if use_streams:
                 done = torch.cuda.Event()

@@ -115,7 +115,7 @@ class LongContextAttention(torch.nn.Module):
         out = self.ring_attn_fn(query_layer, key_layer, value_layer, dropout_p=dropout_p, softmax_scale=softmax_scale,
                                 causal=causal, window_size=window_size, softcap=softcap, alibi_slopes=alibi,
                                 deterministic=deterministic, return_attn_probs=return_attn_probs, group=self.ring_pg,
-                                attn_type=self.attn_type, attn_processor=self.attn_processor,
+                                attn_type=self.attn_type, attn_processor=self.attn_processor, backend="collective",
                                 **_dropout_kw(dropout_p, self.ulysses_pg, query_layer.shape[2]))
         context_layer = out[0] if isinstance(out, tuple) else out
         # (B, S/R, H/U, D) -> (B, S/P, H, D)
@@ -157,7 +157,7 @@ class LongContextAttentionQKVPacked(torch.nn.Module):
                                 window_size=window_size, softcap=softcap,
                                 alibi_slopes=_slice_alibi(alibi_slopes, self.ulysses_pg), deterministic=deterministic,
                                 return_attn_probs=return_attn_probs, group=self.ring_pg, attn_type=self.attn_type,
-                                **_dropout_kw(dropout_p, self.ulysses_pg, qkv.shape[3]))
+                                backend="collective", **_dropout_kw(dropout_p, self.ulysses_pg, qkv.shape[3]))
         out = out[0] if isinstance(out, tuple) else out
         if U > 1:
             out = SeqAllToAll4D.apply(self.ulysses_pg, out, self.gather_idx, self.scatter_idx - 1, self.use_sync)

@@ -10,7 +10,7 @@
 
 namespace lca {
 
-constexpr int kMaxSeg = 32;
+constexpr int kMaxSeg = 128;      // kernel parameters are ~12 KiB with 128 segments per side (limit 32 KiB since CUDA 12.1)
 
 struct QSegD {
   int row0;        // first row of the segment in the Q tensor (dim S)

@@ -385,10 +385,11 @@ static __device__ __noinline__ void comm_cta_bulk(const CommParams& c, uint32_t 
   pp.stage0 = smem_base;
   pp.bar0 = smem_base + kPushStages * kPushStageBytes;
   pp.loads = pp.stores = 0;
-  if (lane == 0) {
-    for (int s = 0; s < kPushStages; ++s) mbar_init(pp.bar0 + 8 * s, 1);
-    fence_mbar_init();
-  }
+  // one barrier per lane: with a warp-uniform address under `if (lane == 0)` ptxas (12.9) if-converts the block, picks
+  // the uniform-datapath form of SYNCS.EXCH and then drops it (`@!P1 NOP` in the SASS) -- the first arrive.expect_tx
+  // on the never-initialised barrier then faults.  Per-lane addresses force the vector form.
+  if (lane < kPushStages) mbar_init(pp.bar0 + 8 * lane, 1);
+  fence_mbar_init();
   __syncwarp();
   const long long row_off_kv = (static_cast<long long>(c.r) * c.U + c.u) * c.rows;
   const long long row_off_q = static_cast<long long>(c.u) * c.rows;
@@ -466,9 +467,7 @@ static __device__ __noinline__ void comm_cta_bulk(const CommParams& c, uint32_t 
       }
     }
   }
-  if (lane == 0) {
-    for (int s = 0; s < kPushStages; ++s) mbar_inval(pp.bar0 + 8 * s);
-  }
+  if (lane < kPushStages) mbar_inval(pp.bar0 + 8 * lane);
   __syncwarp();
   // my output buffer is complete once every compute rank has scattered its tiles into it
   if (wait_o && cta == 0 && lane == 0 && c.o_target != 0) spin_until_ge(c.my_sig + kSigODone, c.o_target, 64, c.watchdog_ns);

@@ -149,7 +149,7 @@ def _rows(spec: PosSpec) -> List[Tuple[int, int, int, int]]:
     return out
 
 
-MAX_SEG = 32
+MAX_SEG = 128
 
 
 def window_bounds(p) -> Tuple[int, int]:

@@ -50,11 +50,32 @@ def get_ulysses_engine_if_supported(group, q, strict: bool = False):
     return engine_for_ulysses_group(group, q, strict)
 
 
+def get_ring_engine_if_supported(group, q, strict: bool = False):
+    try:
+        from .fused_engine import engine_for_ring_group
+    except ImportError:
+        if strict:
+            raise
+        return None
+    return engine_for_ring_group(group, q, strict)
+
+
+def resolve_backend(requested: Optional[str]) -> str:
+    b = requested or os.environ.get("LCA_B200_BACKEND", "auto")
+    if b not in ("auto", "fused", "collective"):
+        raise ValueError(f"backend must be auto|fused|collective, got {b!r}")
+    return b
+
+
 def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dropout_p, softmax_scale, causal,
-              window_size, softcap, alibi_slopes, deterministic) -> Optional[torch.Tensor]:
-    """Run one attention call on the fused engine.  ``kind``: "mesh" (``pg`` = PROCESS_GROUP state) or "ulysses"
-    (``pg`` = the sequence process group).  Returns ``None`` when the caller has to take the collective path."""
+              window_size, softcap, alibi_slopes, deterministic, cu_seqlens=None, return_lse: bool = False):
+    """Run one attention call on the fused engine.  ``kind``: "mesh" (``pg`` = PROCESS_GROUP state), "ulysses"
+    (``pg`` = the sequence process group) or "ring" (``pg`` = a ring group; ``cu_seqlens`` = cumulative LOCAL lengths
+    of a packed variable-length shard).  Returns ``None`` when the caller has to take the collective path, else the
+    output (``return_lse``: ``(out, lse (B, H, rows))``)."""
     if backend == "collective" or getattr(attn_type, "value", "").startswith("torch"):
+        return None
+    if not q.is_cuda:
         return None
     strict = backend == "fused"
     dropout_p = float(dropout_p or 0.0)
@@ -65,9 +86,21 @@ def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dro
             return None
         if _d.p8_of(dropout_p) == 0:
             dropout_p = 0.0
-    eng = get_engine_if_supported(pg, q, strict) if kind == "mesh" else get_ulysses_engine_if_supported(pg, q, strict)
+    if kind == "mesh":
+        eng = get_engine_if_supported(pg, q, strict)
+    elif kind == "ulysses":
+        eng = get_ulysses_engine_if_supported(pg, q, strict)
+    else:
+        eng = get_ring_engine_if_supported(pg, q, strict)
     if eng is None:
         return None
+    if cu_seqlens is not None:
+        cu_seqlens = [int(x) for x in (cu_seqlens.tolist() if torch.is_tensor(cu_seqlens) else cu_seqlens)]
+        if eng.U != 1 or eng.too_many_segments(variant, q.shape[1], cu_seqlens):
+            if strict:
+                raise RuntimeError("fused backend: packed batch has more sequence segments than one launch takes")
+            _note_once(("segs", len(cu_seqlens)), "fused backend skipped: too many packed sequences for one launch")
+            return None
     if not eng.supports_shapes(q, k):
         if strict:
             raise RuntimeError(f"fused backend cannot take q {tuple(q.shape)} / k {tuple(k.shape)} on a "
@@ -84,4 +117,4 @@ def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dro
     seed = eng.dropout_seed() if dropout_p > 0.0 else 0
     with nvtx_range(f"lca.fused.{kind}.{variant}"):
         return eng.attention(q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
-                             dropout_p, seed)
+                             dropout_p, seed, cu_seqlens, return_lse)

@@ -41,7 +41,7 @@ from ..ops import native
 from ..ops.attention import AttnParams
 from ..utils.logging import get_logger
 from ..utils.profiling import nvtx_range
-from .layout import Seg, canonical_variant, ring_positions
+from .layout import Seg, canonical_variant, ring_positions, varlen_positions
 
 _LOG = get_logger()
 
@@ -309,7 +309,7 @@ class FusedUSPEngine:
         return int(t.item())
 
     # ------------------------------------------------------------------------------ forward
-    def forward(self, q, k, v, variant: str, p: AttnParams, need_bwd: bool = True):
+    def forward(self, q, k, v, variant: str, p: AttnParams, need_bwd: bool = True, cu=None):
         """q (B, S/P, H, D), k/v (B, S/P, Hkv, D) local shards -> out (B, S/P, H, D), lse (B, H/U, S/R)."""
         C = native.ext()
         U, R, u, r, P = self.U, self.R, self.u, self.r, self.P
@@ -337,8 +337,8 @@ class FusedUSPEngine:
             out_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
         lse = torch.empty((B, Hl, Sr), dtype=torch.float32, device=q.device)
 
-        qsegs, n_my_tiles = self._q_segments(variant, rows, push_q, self.off_o, self.off_lse_own if push_q else None)
-        ksegs = self._k_segments(variant, rows)
+        qsegs, n_my_tiles = self._q_segments(variant, rows, push_q, self.off_o, self.off_lse_own if push_q else None, cu)
+        ksegs = self._k_segments(variant, rows, cu)
         qstride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
         alibi = self._alibi(p, Hl)
@@ -367,12 +367,24 @@ class FusedUSPEngine:
             return None
         return alibi.to(device=self.device, dtype=torch.float32)[..., self.u * Hl:(self.u + 1) * Hl].contiguous()
 
-    def _q_segments(self, variant, rows, pushed: bool, off_out: int, off_lse=None):
+    def _pos_of(self, variant, rows, cu=None):
+        """ring rank -> position segments of that rank's gathered block (dense layout, or packed varlen sequences:
+        ``cu`` = cumulative LOCAL sequence lengths, one attention group per sequence; ring-only meshes)."""
+        Sr = self.U * rows
+        if cu is None:
+            return lambda rr: ring_positions(variant, rr, self.R, Sr)
+        if self.U != 1:
+            raise ValueError("packed variable-length batches are supported on ring-only meshes (U == 1)")
+        if int(cu[-1]) != rows:
+            raise ValueError(f"cu_seqlens ends at {int(cu[-1])} but the local shard has {rows} tokens")
+        return lambda rr: varlen_positions(variant, rr, self.R, cu)
+
+    def _q_segments(self, variant, rows, pushed: bool, off_out: int, off_lse=None, cu=None):
         """Rows of my gathered Q (ring rank r) split by source shard -> kernel q segments
         [row0, nrows, pos0, flag, o_row0, o_base, o_sig, group]; also the number of 128-row tiles over MY rows."""
         U, R, u, r = self.U, self.R, self.u, self.r
         segs, n_my_tiles = [], 0
-        pos = ring_positions(variant, r, R, U * rows)
+        pos = self._pos_of(variant, rows, cu)(r)
         for su in range(U):
             owner = r * U + su
             for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
@@ -382,7 +394,7 @@ class FusedUSPEngine:
                     flag = SIG_Q + su
                 else:
                     o_base, o_sig, flag = 0, 0, -1
-                seg = [row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, 0]
+                seg = [row0, s.count, s.start, flag, row0 - su * rows, o_base, o_sig, s.group]
                 if off_lse is not None:
                     seg.append(self.slab.peer_ptrs[owner] + off_lse)
                 segs.append(seg)
@@ -391,39 +403,45 @@ class FusedUSPEngine:
         segs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
         return segs, n_my_tiles
 
-    def _k_segments(self, variant, rows):
+    def _k_segments(self, variant, rows, cu=None):
         """All K/V rows in my staging (every source shard) -> [row0, nrows, pos0, flag, group], own block first."""
         U, R, u, r = self.U, self.R, self.u, self.r
         Sr = U * rows
+        pos_of = self._pos_of(variant, rows, cu)
         segs = []
         for sr in [(r - i) % R for i in range(R)]:        # own ring block first, then "ring step" order
-            pos = ring_positions(variant, sr, R, Sr)
+            pos = pos_of(sr)
             us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
             for su in us:
                 for s, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
-                    segs.append([sr * Sr + row0, s.count, s.start, SIG_KV + sr * U + su, 0])
+                    segs.append([sr * Sr + row0, s.count, s.start, SIG_KV + sr * U + su, s.group])
         return segs
 
-    def _bwd_segments(self, variant: str, rows: int):
+    def _bwd_segments(self, variant: str, rows: int, cu=None):
         """Every token shard of the mesh as a segment list over the (B, S, ...) all-rank staging layout of the
         owner-computes backward -> (all_segs, mine, tiles_of_me); a segment is (src sp-rank, staging row0, nrows,
-        global position of its first token).  ``mine`` = segments of my ring block (the stationary rows of both
-        passes); ``tiles_of_me`` = 128-row tiles the whole mesh produces for tokens I own (completion count)."""
+        global position of its first token, attention group).  ``mine`` = segments of my ring block (the stationary
+        rows of both passes); ``tiles_of_me`` = 128-row tiles the whole mesh produces for tokens I own (completion
+        count)."""
         U, R, u, r = self.U, self.R, self.u, self.r
         Sr = U * rows
+        pos_of = self._pos_of(variant, rows, cu)
         all_segs = []
         for sr in [(r - i) % R for i in range(R)]:        # own ring block first, then "ring step" order
-            pos = ring_positions(variant, sr, R, Sr)
+            pos = pos_of(sr)
             us = [u] + [x for x in range(U) if x != u] if sr == r else list(range(U))
             for su in us:
                 for sg, row0 in _slices_with_rows(pos, su * rows, (su + 1) * rows):
-                    all_segs.append((sr * U + su, sr * Sr + row0, sg.count, sg.start))
+                    all_segs.append((sr * U + su, sr * Sr + row0, sg.count, sg.start, sg.group))
         mine = [t for t in all_segs if t[0] // U == r]
-        tiles_of_me = sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == self.me)
+        tiles_of_me = sum((n + 127) // 128 for (src, _, n, _, _) in all_segs if src == self.me)
         return all_segs, mine, tiles_of_me
 
+    def too_many_segments(self, variant, rows, cu) -> bool:
+        return len(self._k_segments(variant, rows, cu)) > native.MAX_SEG
+
     # ------------------------------------------------------------------------------ backward
-    def backward(self, dout, q, k, v, out, lse, lse_own, variant: str, p: AttnParams):
+    def backward(self, dout, q, k, v, out, lse, lse_own, variant: str, p: AttnParams, cu=None):
         """Owner-computes backward (default whenever ``Hkv % U == 0``).
 
         dQ pass kernel: push CTAs send q, dO (+ delta, lse2) head-slices to EVERY sp-rank and k, v likewise; compute
@@ -434,7 +452,7 @@ class FusedUSPEngine:
         in 16-bit like dQ."""
         U = self.U
         if k.shape[2] % U:
-            return self.backward_reduce(dout, q, k, v, out, lse, variant, p)
+            return self.backward_reduce(dout, q, k, v, out, lse, variant, p, cu)
         C = native.ext()
         R, u, r, P = self.R, self.u, self.r, self.P
         B, rows, H, D = q.shape
@@ -462,11 +480,11 @@ class FusedUSPEngine:
         stride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
         alibi = self._alibi(p, Hl)
-        all_segs, mine, tiles_of_me = self._bwd_segments(variant, rows)
-        ksegs = [[row0, n, pos0, SIG_KV + src, 0] for (src, row0, n, pos0) in all_segs]
+        all_segs, mine, tiles_of_me = self._bwd_segments(variant, rows, cu)
+        ksegs = [[row0, n, pos0, SIG_KV + src, grp] for (src, row0, n, pos0, grp) in all_segs]
         # ---- pass 1: dQ of my ring block's queries (stationary) against all K/V (streamed)
-        xq = [[row0, n, pos0, 0, row0 - src * rows, SIG_QA + src, slab.peer_ptrs[src] + self.off_o, 0,
-               self.sig.peer_ptrs[src] + 4 * SIG_ODONE] for (src, row0, n, pos0) in sorted(mine, key=lambda t: -t[3])]
+        xq = [[row0, n, pos0, grp, row0 - src * rows, SIG_QA + src, slab.peer_ptrs[src] + self.off_o, 0,
+               self.sig.peer_ptrs[src] + 4 * SIG_ODONE] for (src, row0, n, pos0, grp) in sorted(mine, key=lambda t: -t[3])]
         self.o_total += U * B * Hl * tiles_of_me * 2
         self._arm_dropout(p, Hl)
         C.usp_bwd_pass(False, q_all, do_all, kst, vst, xq, ksegs, stride, stride, lse2_all, delta_all, dq_own, None, 0,
@@ -475,9 +493,9 @@ class FusedUSPEngine:
                        [self.off_k, self.off_v], [delta_local, lse2_local], [self.off_delta, self.off_lse2], True, Sr, S,
                        self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
         # ---- pass 2: dK/dV of my ring block's keys (stationary) against EVERY rank's queries (streamed)
-        xk = [[row0, n, pos0, 0, row0 - src * rows, SIG_KV + src, slab.peer_ptrs[src] + self.off_dk,
-               slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0) in mine]
-        yq = [[row0, n, pos0, SIG_QA + src, 0] for (src, row0, n, pos0) in all_segs]
+        xk = [[row0, n, pos0, grp, row0 - src * rows, SIG_KV + src, slab.peer_ptrs[src] + self.off_dk,
+               slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0, grp) in mine]
+        yq = [[row0, n, pos0, SIG_QA + src, grp] for (src, row0, n, pos0, grp) in all_segs]
         self.dkv_total += U * B * Hkvl * tiles_of_me * 2
         self._arm_dropout(p, Hl)
         C.usp_bwd_pass(True, kst, vst, q_all, do_all, xk, yq, stride, stride, lse2_all, delta_all, dk_own, dv_own, 0,
@@ -486,7 +504,7 @@ class FusedUSPEngine:
         C.symm_wait(self.sig.ptr + 4 * SIG_DKV, self.dkv_total & 0xFFFFFFFF)
         return dq_own.clone(), dk_own.clone(), dv_own.clone()
 
-    def backward_reduce(self, dout, q, k, v, out, lse, variant: str, p: AttnParams):
+    def backward_reduce(self, dout, q, k, v, out, lse, variant: str, p: AttnParams, cu=None):
         """Reduction backward (used when kv heads are replicated across Ulysses ranks, ``Hkv < U``): every compute rank
         forms partial dK/dV for all K/V rows it holds and reduces them into the owners' fp32 accumulators with
         ``red.global.add.v4.f32`` over NVLink."""
@@ -519,8 +537,8 @@ class FusedUSPEngine:
             dq_local = torch.empty((B, rows, H, D), dtype=q.dtype, device=q.device)
         self.epoch += 1
         fe = self.epoch * self.n_comm
-        qsegs, n_my_tiles = self._q_segments(variant, rows, pushed, self.off_o)
-        ksegs = self._k_segments(variant, rows)
+        qsegs, n_my_tiles = self._q_segments(variant, rows, pushed, self.off_o, None, cu)
+        ksegs = self._k_segments(variant, rows, cu)
         stride = R if canonical_variant(variant) == "stripe" else 1
         wl, wr = native.window_bounds(p)
         alibi = self._alibi(p, Hl)
@@ -560,12 +578,14 @@ class FusedUSPEngine:
 
     # ------------------------------------------------------------------------------ autograd entry
     def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
-                  dropout_p: float = 0.0, dropout_seed: int = 0):
+                  dropout_p: float = 0.0, dropout_seed: int = 0, cu_seqlens=None, return_lse: bool = False):
         p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
         if p.dropout_p > 0.0:        # EXPERIMENTAL (native.dropout_supported): the mask needs no communication at all
             from dataclasses import replace
             p = replace(p, dropout_seed=int(dropout_seed))
-        return _FusedAttnFunc.apply(q, k, v, self, canonical_variant(variant), p)
+        cu = None if cu_seqlens is None else tuple(int(x) for x in cu_seqlens)
+        out, lse = _FusedAttnFunc.apply(q, k, v, self, canonical_variant(variant), p, cu)
+        return (out, lse) if return_lse else out
 
     def _arm_dropout(self, p: AttnParams, Hl: int) -> None:
         """Hand the dropout key to the NEXT fused launch: local query head h of this rank is global head u*Hl + h."""
@@ -601,22 +621,24 @@ _SelfGroup = _SelfGroupType()
 
 class _FusedAttnFunc(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams):
-        out, lse, lse_own = eng.forward(q, k, v, variant, p, need_bwd=any(ctx.needs_input_grad[:3]))
+    def forward(ctx, q, k, v, eng: FusedUSPEngine, variant: str, p: AttnParams, cu=None):
+        out, lse, lse_own = eng.forward(q, k, v, variant, p, need_bwd=any(ctx.needs_input_grad[:3]), cu=cu)
         ctx.save_for_backward(q, k, v, out, lse, lse_own)
-        ctx.eng, ctx.variant, ctx.p = eng, variant, p
-        return out
+        ctx.eng, ctx.variant, ctx.p, ctx.cu = eng, variant, p, cu
+        ctx.mark_non_differentiable(lse_own)
+        return out, lse_own           # lse_own: (B, H, rows) fp32 LSE of MY tokens (all heads)
 
     @staticmethod
-    def backward(ctx, dout):
-        """Collective backward (NCCL a2a + ring P2P around the tcgen05 backward kernels)."""
+    def backward(ctx, dout, _dlse=None):
+        """Owner-computes fused backward; ``LCA_B200_FUSED_BWD=0``: collective backward (NCCL a2a + ring P2P around
+        the tcgen05 backward kernels)."""
         from .all_to_all import all_to_all_4D
         from .ring_attention import ring_attn_backward
         q, k, v, out, lse, lse_own = ctx.saved_tensors
         eng, p = ctx.eng, ctx.p
         if eng.with_bwd:
-            dq, dk, dv = eng.backward(dout, q, k, v, out, lse, lse_own, ctx.variant, p)
-            return dq, dk, dv, None, None, None
+            dq, dk, dv = eng.backward(dout, q, k, v, out, lse, lse_own, ctx.variant, p, ctx.cu)
+            return dq, dk, dv, None, None, None, None
         ug, rg = eng.ulysses_pg, eng.ring_pg
         if eng.U > 1 and k.shape[2] % eng.U:
             raise NotImplementedError("backward with kv_heads < ulysses degree needs the fused backward (round 2)")
@@ -629,9 +651,10 @@ class _FusedAttnFunc(torch.autograd.Function):
         pl = replace(p, alibi_slopes=alibi, head_offset=eng.u * (q.shape[2] // eng.U) if eng.U > 1 else p.head_offset)
         if eng.R == 1:      # no ring dimension: `None` would mean the WORLD group to the ring loop
             rg = _SelfGroup
-        dq, dk, dv = ring_attn_backward(rg, a2a(dout), a2a(q), a2a(k), a2a(v), a2a(out), lse, ctx.variant, pl)
+        dq, dk, dv = ring_attn_backward(rg, a2a(dout), a2a(q), a2a(k), a2a(v), a2a(out), lse, ctx.variant, pl, None, 0,
+                                        ctx.cu, ctx.cu)
         back = (lambda t: all_to_all_4D(t.contiguous(), 1, 2, group=ug)) if eng.U > 1 else (lambda t: t)
-        return back(dq), back(dk), back(dv), None, None, None
+        return back(dq), back(dk), back(dv), None, None, None, None
 
 
 # ---------------------------------------------------------------------------------- factories
@@ -685,6 +708,33 @@ def engine_for_mesh(pgs, q, strict: bool = False):
             eng = FusedUSPEngine(pgs.SP_PG, mesh.ulysses_degree, mesh.ring_degree, mesh.ulysses_rank, mesh.ring_rank,
                                  q.device)
             eng.ulysses_pg, eng.ring_pg = pgs.ULYSSES_PG, pgs.RING_PG
+            _ENGINES[key] = eng
+    return _ENGINES[key]
+
+
+def engine_for_ring_group(group, q, strict: bool = False):
+    """Engine for a bare ring group (``ring_flash_attn_*_func(group=...)``, the varlen entry points): U = 1."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    if type(group).__name__ == "_SelfGroupType":
+        return None
+    world = dist.get_world_size(group)
+    if world == 1:
+        return None
+    if not _supported_input(q) or world > MAX_PEERS:
+        if strict:
+            raise RuntimeError("fused backend unavailable for this input/group")
+        return None
+    key = ("ring", id(group), q.device.index)
+    if key not in _ENGINES:
+        g = group if group is not None else dist.group.WORLD
+        if not _same_node_p2p(g, q.device):
+            if strict:
+                raise RuntimeError("fused backend needs all ranks on one node with P2P access")
+            _ENGINES[key] = None
+        else:
+            eng = FusedUSPEngine(g, 1, world, 0, dist.get_rank(g), q.device)
+            eng.ulysses_pg, eng.ring_pg = None, g
             _ENGINES[key] = eng
     return _ENGINES[key]
 

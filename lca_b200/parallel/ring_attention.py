@@ -174,7 +174,16 @@ def _make_funcs(variant: str):
 
     def func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
              alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
-             attn_processor=None, head_offset=0, dropout_seed=None):
+             attn_processor=None, head_offset=0, dropout_seed=None, backend=None):
+        """``backend``: "auto" (default, ``LCA_B200_BACKEND``) runs the ring on the fused NVLink engine when the group
+        is P2P-reachable on one node (push CTAs + tcgen05 attention in one kernel per rank), else -- and always with
+        "collective" -- the NCCL/gloo P2P ring below."""
+        if head_offset == 0 and dropout_seed is None:
+            from .fused import resolve_backend, try_fused
+            res = try_fused("ring", group, resolve_backend(backend), attn_type, q, k, v, variant, dropout_p, softmax_scale,
+                            causal, window_size, softcap, alibi_slopes, deterministic, None, return_attn_probs)
+            if res is not None:
+                return (res[0], res[1], None) if return_attn_probs else res
         return RingAttnFunc.apply(q, k, v, variant, dropout_p, softmax_scale, causal, window_size, softcap,
                                   alibi_slopes, deterministic, return_attn_probs, group, attn_type, attn_processor,
                                   head_offset, dropout_seed)

@@ -51,7 +51,19 @@ def _make(variant):
     variant = canonical_variant(variant)
 
     def func(q, k, v, cu_seqlens, max_seqlen, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
-             softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None):
+             softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None, attn_type=None,
+             backend=None):
+        """q/k/v ``(total_local, H, D)``; ``backend`` as in the dense ring functions: on an NVLink group the packed
+        shard runs through the fused engine (the kernels take one attention group per sequence), no NCCL P2P, no
+        per-step launches, no LSE merge."""
+        from .fused import resolve_backend, try_fused
+        res = try_fused("ring", group, resolve_backend(backend), attn_type, q.unsqueeze(0), k.unsqueeze(0), v.unsqueeze(0),
+                        variant, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
+                        cu_seqlens, return_attn_probs)
+        if res is not None:
+            if return_attn_probs:
+                return res[0].squeeze(0), res[1].squeeze(0), None
+            return res.squeeze(0)
         return RingVarlenAttnFunc.apply(q, k, v, cu_seqlens, max_seqlen, variant, dropout_p, softmax_scale, causal,
                                         window_size, softcap, alibi_slopes, deterministic, return_attn_probs, group,
                                         attn_type)

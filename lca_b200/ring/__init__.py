@@ -19,13 +19,13 @@ from .utils import flatten_varlen_lse, unflatten_varlen_lse, update_npu_out, upd
 
 def ring_pytorch_attn_func(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1),
                            softcap=0.0, alibi_slopes=None, deterministic=False, return_attn_probs=False, group=None,
-                           attn_type=None, attn_processor=None):
+                           attn_type=None, attn_processor=None, **kw):
     """Basic ring on the pure-PyTorch engine, forward AND backward (reference: ``ring_pytorch_attn.py``,
     whose backward is unreachable)."""
     if attn_type is None or not getattr(attn_type, "value", "").startswith("torch"):
         attn_type = _AttnType.TORCH
     return ring_flash_attn_func(q, k, v, dropout_p, softmax_scale, causal, window_size, softcap, alibi_slopes,
-                                deterministic, return_attn_probs, group, attn_type, attn_processor)
+                                deterministic, return_attn_probs, group, attn_type, attn_processor, **kw)
 
 
 # flashinfer-flavoured entry points of the reference (``ring_flashinfer_attn.py``) -- on B200 they run the

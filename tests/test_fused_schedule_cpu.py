@@ -97,18 +97,18 @@ def test_owner_computes_backward_segments_cover_every_gradient_once(U, R, varian
             e = _engine(U, R, u, r)
             all_segs, mine, tiles_of_me = e._bwd_segments(variant, rows)
             assert len(all_segs) <= 32
-            assert sorted(x for (_, row0, n, _) in all_segs for x in range(row0, row0 + n)) == list(range(S))
+            assert sorted(x for (_, row0, n, _, _) in all_segs for x in range(row0, row0 + n)) == list(range(S))
             hs = slice(u * Hl, (u + 1) * Hl)
             stage = lambda t: t[:, tok_of_stage][:, :, hs]                            # noqa: E731
             qs, ks, vs, dos, outs = (stage(t) for t in (q, k, v, do, out))
             lses = lse[:, hs][:, :, tok_of_stage]
             spos = torch.empty(S, dtype=torch.int64)
-            for (src, row0, n, pos0) in all_segs:
+            for (src, row0, n, pos0, _grp) in all_segs:
                 spos[row0:row0 + n] = pos0 + stride * torch.arange(n)
                 assert row0 // rows == src                                              # staging is sp-rank major
             assert torch.equal(spos, tok_of_stage)                                      # positions == token ids
-            mrows = torch.cat([torch.arange(row0, row0 + n) for (_, row0, n, _) in mine])
-            assert len(mrows) == U * rows and all(src // U == r for (src, _, _, _) in mine)
+            mrows = torch.cat([torch.arange(row0, row0 + n) for (_, row0, n, _, _) in mine])
+            assert len(mrows) == U * rows and all(src // U == r for (src, _, _, _, _) in mine)
             # pass 1: dQ of my ring block (stationary) against everything (streamed)
             bdq, _, _ = attn_block_bwd_ref(dos[:, mrows], qs[:, mrows], ks, vs, outs[:, mrows], lses[:, :, mrows],
                                            spos[mrows], spos, p.softmax_scale, True, win)
@@ -116,7 +116,7 @@ def test_owner_computes_backward_segments_cover_every_gradient_once(U, R, varian
             _, bdk, bdv = attn_block_bwd_ref(dos, qs, ks[:, mrows], vs[:, mrows], outs, lses, spos, spos[mrows],
                                              p.softmax_scale, True, win)
             off = 0
-            for (src, row0, n, pos0) in mine:
+            for (src, row0, n, pos0, _grp) in mine:
                 o_row0 = row0 - src * rows                                              # row inside the owner's shard
                 owner_tok = own[(src % U, src // U)][o_row0:o_row0 + n]
                 assert torch.equal(owner_tok, tok_of_stage[row0:row0 + n])
@@ -128,7 +128,7 @@ def test_owner_computes_backward_segments_cover_every_gradient_once(U, R, varian
                 done_tiles[src] += (n + 127) // 128
                 off += n
             # what this rank waits for: tiles of its own tokens, produced by the U ranks of its ring block
-            assert tiles_of_me == sum((n + 127) // 128 for (src, _, n, _) in all_segs if src == e.me)
+            assert tiles_of_me == sum((n + 127) // 128 for (src, _, n, _, _) in all_segs if src == e.me)
     for name in written:
         assert bool((written[name] == 1).all()), name
     torch.testing.assert_close(dq, rdq[0], atol=1e-5, rtol=1e-5)
@@ -174,3 +174,55 @@ def test_slab_regions_are_disjoint_and_inside_the_allocation(U, R, with_bwd):
                     assert a1 <= b0, f"{an} [{a0},{a1}) overlaps {bn} [{b0},{b1})"
                 assert spans[-1][1] <= total
                 assert all(off % 16 == 0 for off, _, _ in spans)
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("variant", ["basic", "zigzag"])
+def test_varlen_segments_describe_packed_sequences(R, variant):
+    """Packed variable-length shards on a ring-only mesh: the fused engine must hand the kernels one attention group
+    per sequence, with the global positions of the per-sequence ring layout, and the union over all ranks must
+    reproduce per-sequence causal attention exactly (emulated with the fp32 oracle on the segment description)."""
+    H, D = 2, 8
+    glens = [8 * R, 4 * R, 12 * R]                          # global lengths, each divisible by 2R
+    g = torch.Generator().manual_seed(1)
+    seqs = [tuple(torch.randn(1, L, H, D, generator=g) for _ in range(3)) for L in glens]
+    refs = [attention_ref(q, k, v, causal=True)[0] for (q, k, v) in seqs]
+    loc_idx = {rr: [local_token_index(variant, L, 0, rr, 1, R) for L in glens] for rr in range(R)}
+    lens = [len(i) for i in loc_idx[0]]
+    cu = [0]
+    for n in lens:
+        cu.append(cu[-1] + n)
+    rows = cu[-1]
+    # staging of rank r: every source rank's packed shard, sp-rank major
+    pack = lambda rr, j: torch.cat([seqs[i][j][:, loc_idx[rr][i]] for i in range(len(glens))], dim=1)   # noqa: E731
+    k_stage = torch.cat([pack(rr, 1) for rr in range(R)], dim=1)
+    v_stage = torch.cat([pack(rr, 2) for rr in range(R)], dim=1)
+    for r in range(R):
+        e = _engine(1, R, 0, r)
+        qsegs, _ = e._q_segments(variant, rows, False, 0, None, cu)
+        ksegs = e._k_segments(variant, rows, cu)
+        all_segs, mine, tiles = e._bwd_segments(variant, rows, cu)
+        assert {s[4] for s in ksegs} == set(range(len(glens))) and len(all_segs) == len(ksegs)
+        assert sorted(x for s in ksegs for x in range(s[0], s[0] + s[1])) == list(range(R * rows))
+        assert sorted(x for s in qsegs for x in range(s[0], s[0] + s[1])) == list(range(rows))
+        q_loc = pack(r, 0)
+        kpos = torch.empty(R * rows, dtype=torch.int64)
+        kgrp = torch.empty(R * rows, dtype=torch.int64)
+        for row0, n, pos0, flag, grp in ksegs:
+            kpos[row0:row0 + n] = pos0 + torch.arange(n)
+            kgrp[row0:row0 + n] = grp
+            assert flag == SIG_KV + row0 // rows
+        qpos = torch.empty(rows, dtype=torch.int64)
+        qgrp = torch.empty(rows, dtype=torch.int64)
+        for seg in qsegs:
+            row0, n, pos0 = seg[:3]
+            qpos[row0:row0 + n] = pos0 + torch.arange(n)
+            qgrp[row0:row0 + n] = seg[7]
+        out = torch.zeros(1, rows, H, D)
+        for gi in range(len(glens)):                      # one attention group per sequence
+            qm, km = qgrp == gi, kgrp == gi
+            o, _ = attn_block_fwd_ref(q_loc[:, qm], k_stage[:, km], v_stage[:, km], qpos[qm], kpos[km], D ** -0.5, True,
+                                      (-1, -1))
+            out[:, qm] = o
+        want = torch.cat([refs[i][:, loc_idx[r][i]] for i in range(len(glens))], dim=1)
+        torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)

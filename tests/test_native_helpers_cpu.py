@@ -25,7 +25,8 @@ def test_rows_and_strides():
 
 
 def test_chunk_by_group_splits_many_sequences():
-    cu = list(range(0, 41 * 16, 16))                    # 40 sequences of 16 tokens -> 40 groups
+    n = native.MAX_SEG + 8
+    cu = list(range(0, (n + 1) * 16, 16))               # more sequences (= groups) than one launch takes segments
     spec = varlen_positions("basic", 0, 1, cu)
     rows = native._rows(spec)
     chunks = list(native._chunk_by_group(rows, rows))

@@ -90,7 +90,7 @@ def test_dropout_key_is_a_function_of_global_coordinates(seed, b, h, q0, k0):
 
 
 @settings(max_examples=100, deadline=None)
-@given(st.lists(st.integers(1, 3), min_size=1, max_size=40))
+@given(st.lists(st.integers(1, 3), min_size=1, max_size=160))
 def test_chunk_by_group_keeps_groups_whole_and_within_the_segment_budget(segs_per_group):
     """Many-sequence varlen batches are launched in chunks of whole attention groups with <= MAX_SEG segments per side
     (``native._chunk_by_group``): every segment appears exactly once, a group is never split across launches."""
