@@ -113,30 +113,27 @@ struct SchedState {
 // ---- build-time defaults of the opt-in kernel variants: ONE place to flip once a variant has been validated on
 // hardware (tools/validate_experimental.sh).  An environment variable, when set, always overrides the default.
 namespace defaults {
-constexpr int kF32x2 = 1;        // LCA_B200_F32X2      packed fp32x2 softmax / dS arithmetic (validated r2: bwd +4 %, D=64 fwd +22 %)
-constexpr int kBwdSplit = 0;     // LCA_B200_BWD_SPLIT  backward: both warpgroups on every streamed tile
-constexpr int kDynSched = 0;     // LCA_B200_DYN_SCHED  dynamic tile scheduler (push CTAs join the compute pool)
+constexpr int kDynSched = -1;    // LCA_B200_DYN_SCHED  dynamic tile scheduler: -1 = fused launches only (push CTAs join the compute pool)
 constexpr int kPolyEvery = 4;    // LCA_B200_POLY_EVERY exp2 offload ratio of the forward (0, 2*, 3, 4, 6; *packed variant only), head_dim 128
 constexpr int kPolyEveryD64 = 3; //                     the same for head_dim 64
-constexpr int kNoXfix = 0;       // LCA_B200_NO_XFIX    1 = keep the pre-fix dQ-pass kernel (hang reproduction only)
 }  // namespace defaults
 static int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? std::atoi(v) : dflt;
 }
 
-// packed fp32x2 element-wise arithmetic in the softmax / dS stages (EXPERIMENTAL, LCA_B200_F32X2=1)
-static int f32x2_enabled() {
-  static int e = env_int("LCA_B200_F32X2", defaults::kF32x2) == 1 ? 1 : 0;
-  return e;
-}
-static bool dyn_sched_enabled() {
-  static bool e = env_int("LCA_B200_DYN_SCHED", defaults::kDynSched) == 1;
-  return e;
+// Dynamic tile scheduler.  Measured in round 2: on ONE GPU the static snake schedule is 1-4 % faster (CTAs advance in
+// lock-step over neighbouring Q tiles, which keeps K/V tiles hot in L2), on the fused multi-GPU launches dynamic claiming
+// wins (N=2, S=128K forward: 2098 vs 1856 TFLOPS; Ulysses S=32K forward 5.1 vs 7.3 ms) because the push CTAs rejoin
+// the compute pool and late-arriving shards no longer stall a fixed share of the work.  Hence: default on for
+// launches with a communication role, off otherwise; LCA_B200_DYN_SCHED=0/1 forces either.
+static bool dyn_sched_enabled(int n_comm) {
+  static int e = env_int("LCA_B200_DYN_SCHED", defaults::kDynSched);
+  return e < 0 ? n_comm > 0 : e == 1;
 }
 template <typename P>
 static void attach_sched(P& p, const at::Tensor& like, int sms, int n_comm) {
-  if (!dyn_sched_enabled()) return;
+  if (!dyn_sched_enabled(n_comm)) return;
   static std::mutex mu;
   static std::map<int, SchedState> states;
   std::lock_guard<std::mutex> lock(mu);
@@ -246,7 +243,6 @@ static void fill_fwd_params(FwdParams& p, const at::Tensor& q, const at::Tensor&
     // measured r2 (S=32K, packed arithmetic): D=128 is flat in the offload ratio (4: 1.971 ms, 6: 1.978 ms, 3: 2.03 ms);
     // D=64 has twice the exponentials per tensor FLOP and wants the heavier offload (3: 3.01 ms, 6: 3.24 ms, 2: 3.83 ms)
     p.poly_every = poly >= 0 ? poly : (D == 64 ? defaults::kPolyEveryD64 : defaults::kPolyEvery);
-    p.f32x2 = f32x2_enabled();
   }
   p.lse_own_sb = out.size(2) * out.size(1);      // owners keep (B, H_total, rows) next to their (B, rows, H_total, D) output
   p.lse_own_sh = out.size(1);
@@ -274,8 +270,6 @@ static void take_next_dropout(P& p, double softcap) {
   std::vector<int64_t> d;
   d.swap(g_next_drop);
   set_dropout(p, d, softcap);
-  TORCH_CHECK(p.comm.n_comm == 0 || p.comm.peer_slab[kMaxPeers - 1] == nullptr,
-              "native dropout cannot be combined with the experimental push engine / NVLS broadcast yet");
 }
 
 static void fmha_fwd_impl(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
@@ -322,11 +316,8 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
                       int64_t Hkv) {
   TORCH_CHECK(mesh.size() == 7, "mesh arity");
   const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
-  // peer_slabs may carry one extra trailing entry: the NVLS multicast address of the slab (EXPERIMENTAL broadcast push)
-  const bool has_mc = static_cast<int>(peer_slabs.size()) == P + 1;
-  TORCH_CHECK(P == U * R && P <= kMaxPeers && (static_cast<int>(peer_slabs.size()) == P || has_mc) &&
+  TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
               static_cast<int>(peer_sigs.size()) == P, "peer tables");
-  TORCH_CHECK(!has_mc || P < kMaxPeers, "the multicast address travels in the last peer slot");
   c.n_comm = static_cast<int>(mesh[6]);
   TORCH_CHECK(c.n_comm >= 1 && c.n_comm <= 64, "n_comm");
   c.P = P; c.U = U; c.R = R;
@@ -367,7 +358,6 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
     c.peer_slab[i] = reinterpret_cast<unsigned char*>(peer_slabs[i]);
     c.peer_sig[i] = reinterpret_cast<unsigned int*>(peer_sigs[i]);
   }
-  if (has_mc && peer_slabs[P] != 0) c.peer_slab[kMaxPeers - 1] = reinterpret_cast<unsigned char*>(peer_slabs[P]);
   c.my_sig = reinterpret_cast<unsigned int*>(my_sig);
   c.stage_q_rows = stage_q_rows; c.stage_kv_rows = stage_kv_rows;
   c.epoch = static_cast<unsigned int>(epoch);
@@ -497,83 +487,6 @@ void usp_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, cons
 // ------------------------------------------------------------------------------------ fmha bwd
 // One pass of the backward (see fmha_bwd_sm100.cu).  x0/x1 stationary, y0/y1 streamed.
 // xsegs[i] = {row0, nrows, pos0, group, o_row0 [, flag, o_base0, o_base1, o_sig]};  ysegs[i] = {row0, nrows, pos0, flag, group}
-// Counts the 128-row stationary tiles of a launch that have NO visible streamed tile, and those with at most two, under
-// the kernel's own skipping rule (TileIter in fmha_bwd_sm100.cu: a streamed 64-row tile [ka, kb] of the same group is
-// visited unless ka - xmax > wr or xmin - kb > wl).  ka and kb grow with the tile index, so per (stationary tile,
-// streamed segment) the visible tiles are an index interval [lo, hi]: O(1).
-// Why "at most two": the MMA warp issues the first two T GEMM pairs of a work item in its prologue without any
-// warpgroup participation and releases x_empty when the LAST one is issued -- so for such items X can be reloaded (and
-// x_full advance) before a warpgroup that is still in the previous epilogue has waited for this item's phase.
-struct SmallTileCount {
-  int64_t empty = 0, small = 0;      // small includes empty
-};
-static SmallTileCount count_small_stationary_tiles(const BwdParams& p) {
-  constexpr int64_t BXr = 128, BYr = 64;
-  SmallTileCount out;
-  if (p.x_pos_stride <= 0 || p.y_pos_stride <= 0) return out;      // not a layout this library produces
-  for (int xi = 0; xi < p.n_xseg; ++xi) {
-    const XSegD& xs = p.xseg[xi];
-    const int64_t ntx = (xs.nrows + BXr - 1) / BXr;
-    for (int64_t t = 0; t < ntx; ++t) {
-      const int64_t rows = std::min<int64_t>(BXr, xs.nrows - t * BXr);
-      const int64_t xmin = xs.pos0 + t * BXr * p.x_pos_stride;
-      const int64_t xmax = xmin + (rows - 1) * p.x_pos_stride;
-      int64_t visible = 0;
-      for (int yi = 0; yi < p.n_yseg && visible <= 2; ++yi) {
-        const KSegD& ys = p.yseg[yi];
-        if (ys.group != xs.group || ys.nrows <= 0) continue;
-        const int64_t nt = (ys.nrows + BYr - 1) / BYr;
-        const int64_t step = BYr * p.y_pos_stride;               // position step between tile starts (> 0)
-        int64_t lo = 0, hi = nt - 1;
-        if (p.wr >= 0) {                                         // ka(k) = pos0 + k*step <= xmax + wr
-          const int64_t lim = xmax + p.wr - ys.pos0;
-          if (lim < 0) continue;
-          hi = std::min<int64_t>(hi, lim / step);
-        }
-        if (p.wl >= 0) {                                         // kb(k) >= xmin - wl
-          const int64_t need = xmin - p.wl;
-          const int64_t kb_last = ys.pos0 + static_cast<int64_t>(ys.nrows - 1) * p.y_pos_stride;
-          if (kb_last < need) continue;
-          // full tiles: kb(k) = pos0 + k*step + (BYr-1)*stride
-          const int64_t num = need - ys.pos0 - (BYr - 1) * p.y_pos_stride;
-          int64_t k = num <= 0 ? 0 : (num + step - 1) / step;
-          lo = std::min<int64_t>(k, nt - 1);                     // the (possibly partial) last tile reaches kb_last >= need
-        }
-        if (lo <= hi) visible += hi - lo + 1;
-      }
-      if (visible == 0) ++out.empty;
-      if (visible <= 2) ++out.small;
-    }
-  }
-  return out;
-}
-
-// host-only entry for the CPU test-suite: xsegs[i] = {nrows, pos0, group}, ysegs[i] = {nrows, pos0, group}
-std::vector<int64_t> debug_count_small_tiles(const std::vector<std::vector<int64_t>>& xsegs, const std::vector<std::vector<int64_t>>& ysegs,
-                          int64_t x_pos_stride, int64_t y_pos_stride, int64_t wl, int64_t wr) {
-  BwdParams p;
-  std::memset(&p, 0, sizeof(p));
-  TORCH_CHECK(xsegs.size() <= kMaxSeg && ysegs.size() <= kMaxSeg, "segment count");
-  p.n_xseg = static_cast<int>(xsegs.size());
-  p.n_yseg = static_cast<int>(ysegs.size());
-  for (int i = 0; i < p.n_xseg; ++i) {
-    p.xseg[i].nrows = static_cast<int>(xsegs[i].at(0));
-    p.xseg[i].pos0 = static_cast<int>(xsegs[i].at(1));
-    p.xseg[i].group = static_cast<int>(xsegs[i].at(2));
-  }
-  for (int i = 0; i < p.n_yseg; ++i) {
-    p.yseg[i].nrows = static_cast<int>(ysegs[i].at(0));
-    p.yseg[i].pos0 = static_cast<int>(ysegs[i].at(1));
-    p.yseg[i].group = static_cast<int>(ysegs[i].at(2));
-  }
-  p.x_pos_stride = static_cast<int>(x_pos_stride);
-  p.y_pos_stride = static_cast<int>(y_pos_stride);
-  p.wl = static_cast<int>(wl);
-  p.wr = static_cast<int>(wr);
-  const SmallTileCount c = count_small_stationary_tiles(p);
-  return {c.empty, c.small};
-}
-
 static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
                    const at::Tensor& y1, const std::vector<std::vector<int64_t>>& xsegs,
                    const std::vector<std::vector<int64_t>>& ysegs, int64_t x_pos_stride, int64_t y_pos_stride,
@@ -592,11 +505,6 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
               lse2.sizes() == delta.sizes() && lse2.stride(2) == 1 && delta.strides() == lse2.strides(), "lse2/delta");
   TORCH_CHECK(lse2.size(0) == B && lse2.size(1) == Hq, "lse2 shape");
   std::memset(&p, 0, sizeof(p));
-  p.f32x2 = f32x2_enabled();
-  {
-    static int sp = env_int("LCA_B200_BWD_SPLIT", defaults::kBwdSplit) == 1 ? 1 : 0;
-    p.split = sp;
-  }
   make_tmap(&p.tm_x0, x0, "x0", 128);
   make_tmap(&p.tm_x1, x1, "x1", 128);
   make_tmap(&p.tm_y0, y0, "y0", 64);
@@ -666,15 +574,6 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
     TORCH_CHECK(reinterpret_cast<uintptr_t>(p.out1) % 16 == 0, "out1 alignment");
   }
   p.out_mode = static_cast<int>(out_mode);
-  // LCA_B200_NO_XFIX=1 keeps the pre-fix kernel even for launches with empty work items (only to reproduce the hang)
-  static const bool no_xfix = env_int("LCA_B200_NO_XFIX", defaults::kNoXfix) == 1;
-  if (!is_dkv && !no_xfix) {
-    // kXfix whenever a CTA could meet such an item right behind another work item: any empty tile (they come in long
-    // runs in the collective zigzag/stripe ring), or more short items than CTAs (plain causal self-attention has one
-    // two-tile item per (batch, head), each on its own CTA in the last scheduling round: validated kernel stays)
-    const SmallTileCount c = count_small_stationary_tiles(p);
-    p.xfix = (c.empty > 0 || c.small * p.B * p.Hx > num_sms() - 16) ? 1 : 0;   // up to 16 SMs may run push CTAs
-  }
 }
 
 static void fmha_bwd_pass_impl(bool is_dkv, const at::Tensor& x0, const at::Tensor& x1, const at::Tensor& y0,
@@ -865,8 +764,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("usp_bwd_pass", &lca::usp_bwd_pass, "fused USP backward pass (push CTAs / peer scatter / NVLink red.add)");
   m.def("symm_wait", &lca::symm_wait, "device-side wait until a system-scope counter reaches a target");
   m.def("fmha_bwd_pass", &lca::fmha_bwd_pass, "tcgen05 flash-attention backward pass (dQ or dK/dV)");
-  m.def("debug_count_small_tiles", &lca::debug_count_small_tiles,
-        "host-only: {stationary tiles with no visible streamed tile, with at most two} of a dQ-pass launch");
   m.def("set_next_dropout", &lca::set_next_dropout, "EXPERIMENTAL: {p8, seed, head_offset} for the next fused launch");
   m.def("fmha_fwd_drop", &lca::fmha_fwd_drop, "EXPERIMENTAL: forward with coordinate-keyed dropout");
   m.def("fmha_bwd_pass_drop", &lca::fmha_bwd_pass_drop, "EXPERIMENTAL: backward pass with coordinate-keyed dropout");

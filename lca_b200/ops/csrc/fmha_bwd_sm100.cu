@@ -175,35 +175,36 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 
 }  // namespace
 
-// kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring, EXPERIMENTAL); else static snake schedule.
-// kXfix: dQ pass only.  The element-wise warps wait x_full once per work item (their lse2/delta reads must be ordered
-//   after a peer's push), but x_empty is released by the MMA warp alone.  For a work item WITHOUT any visible streamed
-//   tile the MMA warp releases it at once, the producer reloads X, and x_full can complete two phases while a
-//   warpgroup is still in the previous item's epilogue: its one-bit parity wait then blocks forever (found by the
-//   protocol model tests/test_bwd_pipeline_model_cpu.py; matches the one hang seen in round 1: collective zigzag
-//   backward, where early-chunk Q tiles see no key of a later rank's block).  With kXfix every element-wise warp also
-//   arrives on x_empty (count 9) right after its x_full wait, so X cannot be reloaded under a waiter.  The host
-//   selects this instantiation exactly for the launches that contain such empty work items (bindings.cpp), which
-//   leaves the hardware-validated instruction streams in place everywhere else.
-// kSplit (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1): BOTH element-wise warpgroups work on EVERY streamed tile, each on one
-//   32-column half (default: warpgroup wg owns the tiles with j % 2 == wg).  The per-tile critical path
-//   T GEMMs -> element-wise -> accumulate GEMMs gets half as long, which is what bounds the tensor pipe today
-//   (2 stages: utilisation ~ 2*T_mma / (T_mma + T_elementwise)).  The packed 16-bit P / dS of half h is written at
-//   columns [32h, 32h+16) of its stage, i.e. inside the fp32 columns its own warpgroup has already consumed, so the
-//   two warpgroups never touch each other's columns and need no extra barrier; the MMA issuer reads A from there.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk, bool kDrop, bool kSplit, bool kMc, bool kXfix>
+// kDyn: dynamic tile scheduler (global atomic counter + 2-deep smem ring): the default of the fused multi-GPU
+//   launches, where the push CTAs join the compute pool once their transfers are out; else the static snake schedule.
+// kDrop: attention dropout regenerated from global coordinates (scalar arithmetic); every other instantiation runs the
+//   element-wise stage on packed fp32x2 instructions (FFMA2 / FADD2 / FMUL2; statistics are staged NEGATED because the
+//   packed forms take no negate modifier).  Round-2 hardware validation: packed = -4 % time in both passes; the
+//   "both warpgroups on every tile" split (kSplit) and the 64-row forward tiles it was modelled after measured SLOWER
+//   than this pipeline and were deleted.
+// x_empty protocol (dQ pass): the element-wise warps wait x_full once per work item (their lse2/delta reads must be
+//   ordered after a peer's push).  If only the MMA warp released x_empty, a work item WITHOUT any visible streamed tile
+//   would be released at once, the producer would reload X, and x_full could complete two phases while a warpgroup is
+//   still in the previous item's epilogue: its one-bit parity wait would block forever (found by the protocol model
+//   tests/test_bwd_pipeline_model_cpu.py; reproduced on hardware in round 2: tools/gpu_repro_xfix.py hangs with the old
+//   rule, finishes with this one).  So every element-wise warp also arrives on x_empty (count 9) right after its
+//   x_full wait: X cannot be reloaded under a waiter.
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
   using C = Cfg<kD>;
-  // every opt-in variant carries the x_empty fix; only the hardware-validated default keeps the old release rule
-  constexpr bool kXf = (kXfix || kDyn || kPk || kDrop || kSplit || kMc) && !kIsDKV;
+  constexpr bool kXf = !kIsDKV;       // see "x_empty protocol" above
+  constexpr bool kPk = !kDrop;        // packed fp32x2 element-wise stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP backward)
-    comm_role<kMc>(p.comm, smem, !kDyn);
+    comm_role(p.comm, smem, !kDyn);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
-    // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
+    // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8).
+    // The warps that do not drive the TMA unit wait here: the compute prologue below writes the TMEM base address and
+    // its mbarriers into shared memory that the bulk-copy stages are still using.
+    __syncthreads();
   }
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
@@ -264,13 +265,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     mbar_init(acc_empty, 8);
     for (int s = 0; s < 2; ++s) {
       mbar_init(t_full + 8 * s, 1);
-      mbar_init(p_full + 8 * s, kSplit ? 8 : 4);
+      mbar_init(p_full + 8 * s, 4);
     }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(y_full + 8 * s, 1);
       mbar_init(y_empty + 8 * s, 1);
       mbar_init(st_full + 8 * s, 32);
-      mbar_init(st_empty + 8 * s, kSplit ? 8 : 4);
+      mbar_init(st_empty + 8 * s, 4);
     }
     fence_mbar_init();
   }
@@ -373,12 +374,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BY / 16; ++kk)   // acc0 += dS * Y0
-            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + (kSplit ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8),
+            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + kk * 8,
                    make_sw128_desc(y0 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
           if constexpr (kIsDKV) {
 #pragma unroll
             for (int kk = 0; kk < BY / 16; ++kk)   // acc1 += P * Y1
-              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + (kSplit ? (kk >> 1) * 32 + (kk & 1) * 8 : kk * 8),
+              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + kk * 8,
                      make_sw128_desc(y1 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
           }
         };
@@ -448,7 +449,6 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const uint32_t tT0_wg = tmem + lane_base + C::TMEM_T0 + wg * BY;
     const uint32_t tT1_wg = tmem + lane_base + C::TMEM_T1 + wg * BY;
     uint32_t tc = 0, yc = 0, afc = 0, xcw = 0;
-    uint32_t tcs[2] = {0, 0};          // kSplit: per-stage t_full phase counters (both warpgroups see every tile)
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -477,22 +477,14 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         const uint32_t st = yc % C::STAGES;
         const uint32_t ypar = (yc / C::STAGES) & 1;
         ++yc;
-        if constexpr (!kSplit) {
-          if ((j & 1) != wg) { ++j; continue; }
-        }
-        const int sT = kSplit ? (j & 1) : wg;                     // TMEM stage of this tile
-        const uint32_t tT0 = kSplit ? tmem + lane_base + C::TMEM_T0 + sT * BY : tT0_wg;
-        const uint32_t tT1 = kSplit ? tmem + lane_base + C::TMEM_T1 + sT * BY : tT1_wg;
-        const int h_begin = kSplit ? wg : 0, h_end = kSplit ? wg + 1 : 2;   // 32-column halves this warpgroup handles
+        if ((j & 1) != wg) { ++j; continue; }                     // warpgroup wg owns the tiles with j % 2 == wg
+        const int sT = wg;                                        // TMEM stage of this tile
+        const uint32_t tT0 = tT0_wg, tT1 = tT1_wg;
+        constexpr int h_begin = 0, h_end = 2;                     // two 32-column halves per tile
         const int hq = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx;     // query head (ALiBi slope index)
         const float slope = p.alibi ? p.alibi[wk.b * p.alibi_bstride + hq] : 0.f;
-        if constexpr (kSplit) {
-          mbar_wait(t_full + 8 * sT, tcs[sT] & 1);
-          ++tcs[sT];
-        } else {
-          mbar_wait(t_full + 8 * wg, tc & 1);
-          ++tc;
-        }
+        mbar_wait(t_full + 8 * wg, tc & 1);
+        ++tc;
         if constexpr (kIsDKV) mbar_wait(st_full + 8 * st, ypar);
         tc_fence_after();
         const int yb = it.ypos0 + (it.nvalid - 1) * p.y_pos_stride;
@@ -576,8 +568,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
               if constexpr (kIsDKV) {
                 pv[0] = pd[0]; pv[1] = pd[1]; pv[2] = pd[2]; pv[3] = pd[3];
               }
-            } else if constexpr (kPk) {
-              // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair (experimental, LCA_B200_F32X2=1)
+            } else {
+              // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair
               // l2v / dlv hold the NEGATED statistics in this variant: x = T0*mul + (-lse2), d = T1 + (-delta)
               const uint64_t mul2 = ptx::pack_f32x2(mul, mul);
 #pragma unroll
@@ -593,12 +585,6 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
                     ptx::pack_f32x2(dlv[e], dlv[e + 1]));
                 ptx::unpack_f32x2(ptx::mul_f32x2(ptx::pack_f32x2(pv[e], pv[e + 1]), d), dv[e], dv[e + 1]);
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                pv[e] = ex2(fmaf(__uint_as_float(t0[c + e]), mul, -l2v[e]));
-                dv[e] = pv[e] * (__uint_as_float(t1[c + e]) - dlv[e]);
-              }
             }
             if constexpr (kIsDKV) {
               pp[(c >> 1)] = pack2<kBf16>(pv[0], pv[1]);
@@ -607,8 +593,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             ds[(c >> 1)] = pack2<kBf16>(dv[0], dv[1]);
             ds[(c >> 1) + 1] = pack2<kBf16>(dv[2], dv[3]);
           }
-          if constexpr (kIsDKV) tmem_st16(tT0 + half * (kSplit ? 32 : 16), pp);
-          tmem_st16(tT1 + half * (kSplit ? 32 : 16), ds);
+          if constexpr (kIsDKV) tmem_st16(tT0 + half * 16, pp);
+          tmem_st16(tT1 + half * 16, ds);
         }
         tmem_wait_st();
         tc_fence_before();
@@ -684,11 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kPk = false, bool kDrop = false, bool kSplit = false,
-          bool kMc = false, bool kXfix = false>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop = false>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kPk, kDrop, kSplit, kMc, kXfix>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kDrop>;
   // fused launches: the push CTAs stage their bulk copies in the same dynamic shared memory (usp_comm.cuh)
   constexpr int kSmem = C::SMEM_BYTES > kPushSmemBytes ? C::SMEM_BYTES : kPushSmemBytes;
   static bool configured = false;
@@ -707,26 +692,11 @@ static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t str
 
 template <int kD, bool kBf16>
 static cudaError_t launch_pass(const BwdParams& p, bool is_dkv, int num_sms, cudaStream_t stream) {
-  if (p.drop_p8 > 0)                  // experimental dropout variant (static schedule, scalar arithmetic)
-    return is_dkv ? launch_impl<kD, kBf16, true, false, false, true>(p, num_sms, stream)
-                  : launch_impl<kD, kBf16, false, false, false, true>(p, num_sms, stream);
-  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
-    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, false, true>(p, num_sms, stream)
-                  : launch_impl<kD, kBf16, false, false, false, false, false, true>(p, num_sms, stream);
-  if (p.split && !p.dyn_sched) {      // experimental: both warpgroups on every streamed tile (static schedule only)
-    if (p.f32x2)
-      return is_dkv ? launch_impl<kD, kBf16, true, false, true, false, true>(p, num_sms, stream)
-                    : launch_impl<kD, kBf16, false, false, true, false, true>(p, num_sms, stream);
-    return is_dkv ? launch_impl<kD, kBf16, true, false, false, false, true>(p, num_sms, stream)
-                  : launch_impl<kD, kBf16, false, false, false, false, true>(p, num_sms, stream);
-  }
-  if (p.f32x2 && !p.dyn_sched)        // experimental packed element-wise stage (static schedule only)
+  if (p.drop_p8 > 0)                  // dropout instantiations (static schedule, scalar arithmetic)
     return is_dkv ? launch_impl<kD, kBf16, true, false, true>(p, num_sms, stream)
                   : launch_impl<kD, kBf16, false, false, true>(p, num_sms, stream);
   if (p.dyn_sched)
     return is_dkv ? launch_impl<kD, kBf16, true, true>(p, num_sms, stream) : launch_impl<kD, kBf16, false, true>(p, num_sms, stream);
-  if (p.xfix && !is_dkv)              // dQ pass with short / empty work items (see kXfix above); every opt-in variant has it built in
-    return launch_impl<kD, kBf16, false, false, false, false, false, false, true>(p, num_sms, stream);
   return is_dkv ? launch_impl<kD, kBf16, true, false>(p, num_sms, stream) : launch_impl<kD, kBf16, false, false>(p, num_sms, stream);
 }
 

@@ -146,26 +146,29 @@ struct Bars {
 
 // kPolyEvery: 1 of every kPolyEvery element pairs of an unmasked tile uses ex2_poly (0 = MUFU only)
 // kDyn: work items are claimed from a global atomic counter by the producer warp and broadcast to the other roles
-// kDrop: attention dropout regenerated from global coordinates (sm100_ptx.cuh: dropout_*; experimental, opt-in)
-// kMc: the push CTAs broadcast K/V through the slab's NVLS multicast address (usp_comm.cuh; experimental, opt-in)
-// kPk: the unmasked softmax runs on packed fp32x2 instructions (FFMA2 / FADD2): scale-and-subtract, the polynomial
-//      exp2 and the row sum issue once per element pair (experimental, opt-in: LCA_B200_F32X2=1)
-//       through a 2-deep smem ring (EXPERIMENTAL); otherwise the static snake schedule is used.
-template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kPk, bool kDrop, bool kMc>
+//       through a 2-deep smem ring (default of the fused multi-GPU launches: the push CTAs join the compute pool);
+//       otherwise the static snake schedule is used.
+// kDrop: attention dropout regenerated from global coordinates (sm100_ptx.cuh: dropout_*; scalar arithmetic).
+// Every other instantiation runs the softmax on packed fp32x2 instructions (FFMA2 / FADD2): scale-and-subtract, the
+// polynomial exp2 and the row sum issue once per element pair (validated in round 2: D=64 forward -18 % time,
+// D=128 flat; the 64-row-K/V-tile variant this replaced measured 8 % slower and was deleted).
+// Empty work items (no visible K/V tile) hand their Q tiles back through o_full, so q_full can never complete two
+// phases under the MMA warp's parity wait (tests/test_fwd_pipeline_model_cpu.py).
+template <int kD, bool kBf16, int kPolyEvery, bool kDyn, bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_constant__ FwdParams p) {
   using C = Cfg<kD>;
-  // opt-in variants hand the Q tiles of an EMPTY work item (no visible K/V tile) back through o_full, so q_full can
-  // never complete two phases under the MMA warp's parity wait (docs/ROUND2_PLAN.md, "Robustness item"); the
-  // hardware-validated default keeps its original rule (the warpgroup waits q_full itself)
-  constexpr bool kQf = kDyn || kPk || kDrop || kMc;
+  constexpr bool kPk = !kDrop;        // packed fp32x2 softmax arithmetic
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem - smem_u32(smem_raw));
   if (static_cast<int>(blockIdx.x) < p.comm.n_comm) {   // communication role (fused USP path)
-    comm_role<kMc>(p.comm, smem, !kDyn);
+    comm_role(p.comm, smem, !kDyn);
     if constexpr (!kDyn) return;
     // kDyn: work is claimed dynamically, so a push CTA joins the compute pool as soon as its transfers are out
-    // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8)
+    // instead of leaving its SM idle for the rest of the kernel (n_comm of 148 SMs = 5 % at the default of 8).
+    // The warps that do not drive the TMA unit wait here: the compute prologue below writes the TMEM base address and
+    // its mbarriers into shared memory that the bulk-copy stages are still using.
+    __syncthreads();
   }
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
@@ -326,9 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           ++qc[t];
         }
         if (!have) {
-          if constexpr (kQf) {
-            for (int t = 0; t < nt; ++t) mma_commit(B.o_full[t]);
-          }
+          for (int t = 0; t < nt; ++t) mma_commit(B.o_full[t]);      // empty item: hand the Q tiles back
           continue;
         }
         // first tile: S_t = Q_t K_0^T
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + lane_base + C::TMEM_S + t * 128;
     const uint32_t tO = tmem + lane_base + C::TMEM_O + t * kD;
-    uint32_t sc = 0, oc = 0, qc = 0;
+    uint32_t sc = 0, oc = 0;
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -607,14 +608,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
       }
       // ---- epilogue: O / l -> 16-bit -> smem (XOR-swizzled 16B chunks) -> coalesced global stores
       uint8_t* stage = smem_gen + C::OFF_Q + t * C::TILE_BYTES;
-      if (j > 0 || kQf) {
-        mbar_wait(B.o_full[t], oc & 1);
-        ++oc;
-        tc_fence_after();
-      } else {
-        mbar_wait(B.q_full[t], qc & 1);   // Q landed (never consumed): safe to reuse its smem
-      }
-      ++qc;
+      mbar_wait(B.o_full[t], oc & 1);     // committed by the MMA warp for empty items too: Q smem is reusable
+      ++oc;
+      tc_fence_after();
       float inv = (l > 0.f) ? 1.f / l : 0.f;
       if constexpr (kDrop) inv *= p.drop_rscale;
 #pragma unroll
@@ -693,10 +689,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, int kPoly, bool kDyn, bool kPk = false, bool kDrop = false, bool kMc = false>
+template <int kD, bool kBf16, int kPoly, bool kDyn, bool kDrop = false>
 static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<kD>;
-  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kPk, kDrop, kMc>;
+  auto kern = fmha_fwd_kernel<kD, kBf16, kPoly, kDyn, kDrop>;
   // fused launches: the push CTAs stage their bulk copies in the same dynamic shared memory (usp_comm.cuh)
   constexpr int kSmem = C::SMEM_BYTES > kPushSmemBytes ? C::SMEM_BYTES : kPushSmemBytes;
   static bool configured = false;
@@ -713,28 +709,20 @@ static cudaError_t launch_impl(const FwdParams& p, int num_sms, cudaStream_t str
   return cudaGetLastError();
 }
 
+template <int kD, bool kBf16, bool kDyn>
+static cudaError_t launch_sched(const FwdParams& p, int num_sms, cudaStream_t stream) {
+  switch (p.poly_every) {       // exp2 offload ratio: 0 = MUFU only; 3 (head_dim 64 default), 4 (head_dim 128 default), 6
+    case 0: return launch_impl<kD, kBf16, 0, kDyn>(p, num_sms, stream);
+    case 3: return launch_impl<kD, kBf16, 3, kDyn>(p, num_sms, stream);
+    case 6: return launch_impl<kD, kBf16, 6, kDyn>(p, num_sms, stream);
+    default: return launch_impl<kD, kBf16, 4, kDyn>(p, num_sms, stream);
+  }
+}
+
 template <int kD, bool kBf16>
 static cudaError_t launch_poly(const FwdParams& p, int num_sms, cudaStream_t stream) {
-  if (p.drop_p8 > 0) return launch_impl<kD, kBf16, 0, false, false, true>(p, num_sms, stream);   // experimental
-  if (p.comm.n_comm > 0 && p.comm.peer_slab[kMaxPeers - 1] != nullptr)      // experimental push engine / NVLS broadcast
-    return launch_impl<kD, kBf16, 6, false, false, false, true>(p, num_sms, stream);
-  if (p.f32x2 && !p.dyn_sched) {      // experimental packed-softmax instantiations (static schedule only)
-    switch (p.poly_every) {
-      case 0: return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);
-      case 2: return launch_impl<kD, kBf16, 2, false, true>(p, num_sms, stream);   // half of the pairs: D=64 is MUFU-bound 2:1
-      case 3: return launch_impl<kD, kBf16, 3, false, true>(p, num_sms, stream);
-      case 4: return launch_impl<kD, kBf16, 4, false, true>(p, num_sms, stream);
-      default: return launch_impl<kD, kBf16, 6, false, true>(p, num_sms, stream);
-    }
-  }
-  if (p.dyn_sched)
-    return p.poly_every == 0 ? launch_impl<kD, kBf16, 0, true>(p, num_sms, stream) : launch_impl<kD, kBf16, 6, true>(p, num_sms, stream);
-  switch (p.poly_every) {
-    case 0: return launch_impl<kD, kBf16, 0, false>(p, num_sms, stream);
-    case 3: return launch_impl<kD, kBf16, 3, false>(p, num_sms, stream);
-    case 4: return launch_impl<kD, kBf16, 4, false>(p, num_sms, stream);
-    default: return launch_impl<kD, kBf16, 6, false>(p, num_sms, stream);
-  }
+  if (p.drop_p8 > 0) return launch_impl<kD, kBf16, 0, false, true>(p, num_sms, stream);   // dropout: static schedule
+  return p.dyn_sched ? launch_sched<kD, kBf16, true>(p, num_sms, stream) : launch_sched<kD, kBf16, false>(p, num_sms, stream);
 }
 
 cudaError_t launch_fmha_fwd(const FwdParams& p, int head_dim, bool bf16, int num_sms, cudaStream_t stream) {

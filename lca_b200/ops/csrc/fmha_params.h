@@ -106,12 +106,11 @@ struct FwdParams {
   const float* k_scale;               // (B, Hkv, ceil(Sk/128))
   const float* v_scale;               // (B, Hkv)
   int64_t q_scale_sb, q_scale_sh, k_scale_sb, k_scale_sh;
-  // dynamic tile scheduler (kDyn instantiations only; EXPERIMENTAL, LCA_B200_DYN_SCHED=1)
+  // dynamic tile scheduler (kDyn instantiations: default of the fused launches, LCA_B200_DYN_SCHED)
   uint32_t* sched_counter;            // monotonic device counter shared by the compute CTAs of a launch
   uint32_t sched_base;                // counter value at launch start (host-tracked: += total_work + compute CTAs)
   int dyn_sched;
-  int f32x2;                          // packed fp32x2 softmax arithmetic (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
-  // attention dropout (kDrop instantiations; EXPERIMENTAL, LCA_B200_NATIVE_DROPOUT=1): keep decisions are a pure
+  // attention dropout (kDrop instantiations; default for dropout_p > 0 since round 2): keep decisions are a pure
   // function of (seed, batch + group, global query head, global q position, global k position) -- ops/dropout.py
   int drop_p8;                        // 0 = off; a score is dropped when its hash byte < drop_p8
   uint32_t drop_seed;
@@ -164,15 +163,12 @@ struct BwdParams {
   uint32_t* sched_counter;            // dynamic tile scheduler (see FwdParams)
   uint32_t sched_base;
   int dyn_sched;
-  int f32x2;                          // packed fp32x2 element-wise stage (kPk instantiations; EXPERIMENTAL, LCA_B200_F32X2=1)
-  // attention dropout (kDrop instantiations; EXPERIMENTAL, LCA_B200_NATIVE_DROPOUT=1): keep decisions are a pure
+  // attention dropout (kDrop instantiations; default for dropout_p > 0 since round 2): keep decisions are a pure
   // function of (seed, batch + group, global query head, global q position, global k position) -- ops/dropout.py
   int drop_p8;                        // 0 = off; a score is dropped when its hash byte < drop_p8
   uint32_t drop_seed;
   float drop_rscale;                  // 256 / (256 - drop_p8)
   int drop_head_off;                  // global index of local query head 0
-  int split;                          // kSplit instantiations (EXPERIMENTAL, LCA_B200_BWD_SPLIT=1)
-  int xfix;                           // dQ pass: some stationary tile sees no streamed tile -> kXfix instantiation
 };
 
 }  // namespace lca

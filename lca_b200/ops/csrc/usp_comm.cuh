@@ -72,57 +72,9 @@ __device__ __forceinline__ void comm_copy(const CopyMsg& m, int B, int tid, int 
   }
 }
 
-// Copy loop of the EXPERIMENTAL push engine (comm_cta<true>): 8 x 16 B in flight per thread instead of 4 (the plain
-// loop is latency-bound at ~25 GB/s per CTA), row/column split by shift when the row length is a power of two
-// (it is for every head_dim x heads combination in use) instead of two 64-bit divisions per vector.
-// kStrong: the destination is an NVLS *multicast* address (one store is replicated by the NVSwitch into every rank's
-// slab); multimem addresses must be written with multimem.st (SASS: STG.E.128.STRONG.SYS).
-template <bool kStrong>
-__device__ __forceinline__ void comm_copy_fast(const CopyMsg& m, int B, int tid, int nthreads) {
-  constexpr int UNR = 8;
-  const unsigned rv = static_cast<unsigned>(m.row_vecs);
-  const unsigned nrows = static_cast<unsigned>(m.nrows);
-  const unsigned long long total = static_cast<unsigned long long>(B) * nrows * rv;
-  const bool pow2 = (rv & (rv - 1u)) == 0u;
-  const int sh = 31 - __clz(static_cast<int>(rv));
-  const unsigned long long step = static_cast<unsigned long long>(nthreads >> 5) * (32 * UNR);
-  for (unsigned long long base = static_cast<unsigned long long>(tid >> 5) * (32 * UNR) + (tid & 31); base < total;
-       base += step) {
-    uint4 val[UNR];
-    long long doff[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; ++j) {
-      const unsigned long long i = base + 32ull * j;      // a warp reads 512 contiguous bytes per j
-      doff[j] = -1;
-      if (i < total) {
-        const unsigned long long br = pow2 ? (i >> sh) : (i / rv);
-        const unsigned c = static_cast<unsigned>(i - br * rv);
-        unsigned b = 0, row = static_cast<unsigned>(br);
-        if (B > 1) { b = row / nrows; row -= b * nrows; }
-        val[j] = *reinterpret_cast<const uint4*>(m.src + b * m.src_sb + row * m.src_ss + c * 16ll);
-        doff[j] = b * m.dst_sb + row * m.dst_ss + c * 16ll;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; ++j) {
-      if (doff[j] < 0) continue;
-      if constexpr (kStrong) {
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m.dst + doff[j]),
-                     "f"(__uint_as_float(val[j].x)), "f"(__uint_as_float(val[j].y)), "f"(__uint_as_float(val[j].z)),
-                     "f"(__uint_as_float(val[j].w))
-                     : "memory");
-      } else {
-        *reinterpret_cast<uint4*>(m.dst + doff[j]) = val[j];
-      }
-    }
-  }
-}
-
-// kMc (EXPERIMENTAL; LCA_B200_FAST_PUSH=1: faster copy loops only; LCA_B200_NVLS=1 with the VMM slab: broadcast too):
-// when the host put the slab's NVLS multicast address into
-// peer_slab[kMaxPeers - 1], everything that goes to EVERY rank (K/V; in the owner-computes backward also Q, dO and the
-// row statistics) is written ONCE to the multicast window instead of P times to unicast peers: NVLink egress / P.
-template <bool kMc>
+// Legacy scalar push engine (CommParams::push_mode == 0, LCA_B200_PUSH=scalar): every thread of the push CTAs moves
+// 16-byte vectors with ld.global / st.global.  ~25 GB/s per CTA (4 x 16 B in flight per thread); kept as the
+// reference implementation the bulk engine below is validated against.
 static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
   using namespace ptx;
   const int tid = static_cast<int>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -133,63 +85,9 @@ static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
     st_release_sys(c.peer_sig[threadIdx.x] + kSigRTR + me, c.epoch);
   const long long row_off_kv = (static_cast<long long>(c.r) * c.U + c.u) * c.rows;
   const long long row_off_q = static_cast<long long>(c.u) * c.rows;
-  bool mc = false;
-  if constexpr (kMc) {
-    unsigned char* mcb = c.peer_slab[kMaxPeers - 1];     // multicast base, or a small sentinel: fast unicast copies only
-    // a head slice per destination exists only when heads are scattered (U > 1); the broadcast needs ONE slice for all
-    mc = (reinterpret_cast<uintptr_t>(mcb) > 4096u) && (c.U == 1);
-    if (mc) {
-      if (static_cast<int>(threadIdx.x) < c.P) spin_until_ge(c.my_sig + kSigRTR + threadIdx.x, c.epoch, 32, c.watchdog_ns);
-      __syncthreads();                    // every rank has entered this call: all staging buffers may be overwritten
-      CopyMsg m;
-      m.nrows = c.rows;
-      m.row_vecs = c.Hkvl * c.D * esz / 16;
-      m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
-      m.dst_sb = c.stage_kv_rows * m.dst_ss;
-      for (int t = 0; t < c.n_kv; ++t) {
-        m.src = static_cast<const unsigned char*>(c.kvt[t].src);
-        m.src_sb = c.kvt[t].sb * esz; m.src_ss = c.kvt[t].ss * esz;
-        m.dst = mcb + c.kvt[t].off + row_off_kv * m.dst_ss;
-        comm_copy_fast<true>(m, c.B, tid, nthreads);
-      }
-      if (c.q_to_all) {
-        m.row_vecs = c.Hl * c.D * esz / 16;
-        m.dst_ss = static_cast<long long>(c.Hl) * c.D * esz;
-        m.dst_sb = c.stage_kv_rows * m.dst_ss;
-        for (int t = 0; t < c.n_q; ++t) {
-          m.src = static_cast<const unsigned char*>(c.qt[t].src);
-          m.src_sb = c.qt[t].sb * esz; m.src_ss = c.qt[t].ss * esz;
-          m.dst = mcb + c.qt[t].off + row_off_kv * m.dst_ss;
-          comm_copy_fast<true>(m, c.B, tid, nthreads);
-        }
-        for (int t = 0; t < c.n_stat; ++t) {
-          CopyMsg s;
-          s.nrows = c.Hl;
-          s.row_vecs = c.rows * 4 / 16;
-          s.src = reinterpret_cast<const unsigned char*>(c.stat[t]);
-          s.src_sb = static_cast<long long>(c.H) * c.rows * 4;
-          s.src_ss = static_cast<long long>(c.rows) * 4;
-          s.dst = mcb + c.stat_off[t] + row_off_kv * 4;
-          s.dst_sb = static_cast<long long>(c.Hl) * c.stage_kv_rows * 4;
-          s.dst_ss = c.stage_kv_rows * 4;
-          comm_copy_fast<true>(s, c.B, tid, nthreads);
-        }
-      }
-      __threadfence_system();
-      __syncthreads();
-    }
-  }
   for (int i = 0; i < c.P; ++i) {
     const int d = (me + i) % c.P;
     const int du = d % c.U, dr = d / c.U;
-    if (mc) {                             // payload already broadcast: only the arrival counters remain
-      if (threadIdx.x == 0) {
-        red_add_release_sys(c.peer_sig[d] + kSigKV + me, 1u);
-        if (dr == c.r) red_add_release_sys(c.peer_sig[d] + kSigQ + c.u, 1u);
-        red_add_release_sys(c.peer_sig[d] + kSigQA + me, 1u);
-      }
-      continue;
-    }
     if (threadIdx.x == 0) {
       spin_until_ge(c.my_sig + kSigRTR + d, c.epoch, 32, c.watchdog_ns);
     }
@@ -205,8 +103,7 @@ static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
       m.src = static_cast<const unsigned char*>(c.kvt[t].src) + static_cast<long long>(h0) * c.D * esz;
       m.src_sb = c.kvt[t].sb * esz; m.src_ss = c.kvt[t].ss * esz;
       m.dst = c.peer_slab[d] + c.kvt[t].off + row_off_kv * m.dst_ss;
-      if constexpr (kMc) comm_copy_fast<false>(m, c.B, tid, nthreads);
-      else comm_copy(m, c.B, tid, nthreads);
+      comm_copy(m, c.B, tid, nthreads);
     }
     const bool have_q = c.n_q > 0 || c.n_stat > 0;
     const bool send_q = have_q && (c.q_to_all || dr == c.r);
@@ -220,8 +117,7 @@ static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
         m.src = static_cast<const unsigned char*>(c.qt[t].src) + static_cast<long long>(du) * c.Hl * c.D * esz;
         m.src_sb = c.qt[t].sb * esz; m.src_ss = c.qt[t].ss * esz;
         m.dst = c.peer_slab[d] + c.qt[t].off + q_off * m.dst_ss;
-        if constexpr (kMc) comm_copy_fast<false>(m, c.B, tid, nthreads);
-        else comm_copy(m, c.B, tid, nthreads);
+        comm_copy(m, c.B, tid, nthreads);
       }
       for (int t = 0; t < c.n_stat; ++t) {   // (B, H, rows) fp32 -> destination (B, Hl, q_rows) at column q_off
         CopyMsg s;
@@ -233,8 +129,7 @@ static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
         s.dst = c.peer_slab[d] + c.stat_off[t] + q_off * 4;
         s.dst_sb = static_cast<long long>(c.Hl) * q_rows * 4;
         s.dst_ss = q_rows * 4;
-        if constexpr (kMc) comm_copy_fast<false>(s, c.B, tid, nthreads);
-        else comm_copy(s, c.B, tid, nthreads);
+        comm_copy(s, c.B, tid, nthreads);
       }
     }
     __threadfence_system();
@@ -474,12 +369,11 @@ static __device__ __noinline__ void comm_cta_bulk(const CommParams& c, uint32_t 
 }
 
 // kernel-side dispatch of the communication role; returns after this CTA's transfers are out
-template <bool kMc>
 __device__ __forceinline__ void comm_role(const CommParams& c, uint32_t smem_base, bool wait_o) {
   if (c.push_mode == 1) {
     comm_cta_bulk(c, smem_base, wait_o);
   } else {
-    comm_cta<kMc>(c, wait_o);
+    comm_cta(c, wait_o);
   }
 }
 

@@ -165,25 +165,15 @@ class FusedUSPEngine:
         self.epoch = 0
         self.o_total = 0
         self.dkv_total = 0
-        self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "8"))
+        # push CTAs: one SM sustains ~70 GB/s of bulk copies into a peer (latency-bound: ~128 KiB in flight), so an NVLink
+        # direction (~750 GB/s) needs >= 12; with the dynamic scheduler they join the compute pool afterwards (measured
+        # N=2: 8 -> 16 CTAs: forward 2064 -> 2098 TFLOPS, Ulysses S=32K forward 5.8 -> 5.1 ms)
+        self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "16"))
         self._refused = set()                   # call shapes whose slab did not fit (decided collectively, once)
         self.slab_bytes = 0
         self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
         self.sig = _make_slab(SIG_BYTES, sp_group, device)
-
-    def _push_ptrs(self, slab):
-        """Peer slab addresses for a launch that carries push CTAs.  EXPERIMENTAL (``LCA_B200_NVLS=1`` together with
-        ``LCA_B200_SLAB=vmm``): on a pure ring (U == 1) the slab's NVLS multicast address rides along as one extra
-        entry and the push CTAs broadcast K/V (backward: also Q, dO, statistics) with ONE store instead of P.
-        ``LCA_B200_FAST_PUSH=1`` alone selects the same experimental push engine (8 x 16 B in flight per thread, no
-        64-bit divisions) with unicast stores, on any mesh and any slab provider."""
-        mc = getattr(slab, "multicast_ptr", 0)
-        if mc and self.U == 1 and self.P < 16 and os.environ.get("LCA_B200_NVLS", "0") == "1":
-            return list(slab.peer_ptrs) + [mc]
-        if self.P < 16 and os.environ.get("LCA_B200_FAST_PUSH", "0") == "1":
-            return list(slab.peer_ptrs) + [1]        # sentinel: experimental push engine, unicast only
-        return slab.peer_ptrs
 
     def close(self) -> None:
         """Release the slabs (collective: peers must have stopped writing)."""
@@ -352,7 +342,7 @@ class FusedUSPEngine:
                   float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
                   [P, U, R, u, r, rows, self.n_comm],
                   [self.off_q, self.off_k, self.off_v, Sr, P * rows],
-                  self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
+                  slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
         if push_q:   # the symmetric buffers are reused by the next call
             out = out_local.clone()
             lse_own = slab.tensor(self.off_lse_own, (B, H, rows), torch.float32).clone()
@@ -491,7 +481,7 @@ class FusedUSPEngine:
                        u * Hl, float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe,
                        [P, U, R, u, r, rows, self.n_comm], [q, dout], [self.off_q, self.off_do], [k, v],
                        [self.off_k, self.off_v], [delta_local, lse2_local], [self.off_delta, self.off_lse2], True, Sr, S,
-                       self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
+                       slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
         # ---- pass 2: dK/dV of my ring block's keys (stationary) against EVERY rank's queries (streamed)
         xk = [[row0, n, pos0, grp, row0 - src * rows, SIG_KV + src, slab.peer_ptrs[src] + self.off_dk,
                slab.peer_ptrs[src] + self.off_dv, self.sig.peer_ptrs[src] + 4 * SIG_DKV] for (src, row0, n, pos0, grp) in mine]
@@ -555,7 +545,7 @@ class FusedUSPEngine:
         C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,
                        float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe, mesh, ql, qo, [k, v],
                        [self.off_k, self.off_v], [delta_local] if pushed else [], [self.off_delta] if pushed else [],
-                       False, Sr, P * rows, self._push_ptrs(slab), self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
+                       False, Sr, P * rows, slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target, H, Hkv)
         # ---- pass 2: dK/dV for every K/V row I hold, reduced into the owners' accumulators
         h0 = u * Hkvl if Hkv >= U else (u * Hkv) // U
         xk, n_my_kv_tiles = [], 0

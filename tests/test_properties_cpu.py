@@ -162,41 +162,3 @@ def test_tile_skipping_never_drops_a_visible_tile(q_pos0, q_rows, q_stride, q_gr
                 assert (si, kt) in visited, (si, kt)
 
 
-@settings(max_examples=300, deadline=None)
-@given(st.lists(st.tuples(st.integers(1, 700), st.integers(0, 3000), st.integers(0, 1)), min_size=1, max_size=3),
-       st.lists(st.tuples(st.integers(1, 700), st.integers(0, 3000), st.integers(0, 1)), min_size=1, max_size=3),
-       st.sampled_from([1, 2, 4]), st.sampled_from([1, 2, 4]), st.integers(-1, 400), st.integers(-1, 400), st.booleans())
-def test_small_work_item_detection_matches_the_kernels_skipping_rule(xdefs, ydefs, xs, ys, wl, wr, causal):
-    """``bindings.cpp: count_small_stationary_tiles`` (O(1) interval arithmetic per tile and segment; decides when the dQ
-    pass takes the ``kXfix`` instantiation) against a brute-force walk of the kernel's ``TileIter`` rule (128-row
-    stationary tiles, 64-row streamed tiles): number of stationary tiles without any / with at most two streamed tiles."""
-    from lca_b200.ops import native
-    if not native.extension_loaded():
-        pytest.skip("extension not built")
-    if causal:
-        wr = 0
-    BX, BY = 128, 64
-    n_empty = n_small = 0
-    for (xn, xp, xg) in xdefs:
-        for t in range((xn + BX - 1) // BX):
-            rows = min(BX, xn - t * BX)
-            xmin = xp + t * BX * xs
-            xmax = xmin + (rows - 1) * xs
-            seen = 0
-            for (yn, yp, yg) in ydefs:
-                if yg != xg:
-                    continue
-                for k in range((yn + BY - 1) // BY):
-                    nv = min(BY, yn - k * BY)
-                    ka = yp + k * BY * ys
-                    kb = ka + (nv - 1) * ys
-                    if wr >= 0 and ka - xmax > wr:
-                        break
-                    if wl >= 0 and xmin - kb > wl:
-                        continue
-                    seen += 1
-            n_empty += seen == 0
-            n_small += seen <= 2
-    got = native.ext().debug_count_small_tiles([list(x) for x in xdefs], [list(y) for y in ydefs], xs, ys, wl, wr)
-    assert got[0] == n_empty
-    assert got[1] == n_small
