@@ -27,7 +27,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def parse():
+PRESETS = {
+    2: dict(seq=32 * 1024, heads=32, ulysses=8, ring_impl="basic"),
+    3: dict(seq=256 * 1024, heads=8, ulysses=1, ring_impl="zigzag"),
+    4: dict(seq=128 * 1024, heads=32, kv_heads=4, ulysses=2, ring_impl="zigzag", window=8192),
+    5: dict(seq=64 * 1024, heads=16, ulysses=4, ring_impl="zigzag", qkvpacked=True),
+}
+
+
+def parse(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -55,16 +64,13 @@ def parse():
                          "4: U=2 x ring zigzag GQA kv=4 S=128K window; 5: U=4 x ring qkvpacked S=64K h=16); explicit flags win")
     ap.add_argument("--fp8", action="store_true", help="ours: e4m3 block-scaled forward (config 5); backward stays bf16")
     ap.add_argument("--no-check", action="store_true", help="skip the fp32 sampled-row correctness check after the timed regions")
-    a = ap.parse_args()
-    presets = {
-        2: dict(seq=32 * 1024, heads=32, ulysses=8, ring_impl="basic"),
-        3: dict(seq=256 * 1024, heads=8, ulysses=1, ring_impl="zigzag"),
-        4: dict(seq=128 * 1024, heads=32, kv_heads=4, ulysses=2, ring_impl="zigzag", window=8192),
-        5: dict(seq=64 * 1024, heads=16, ulysses=4, ring_impl="zigzag", qkvpacked=True),
-    }
+    ap.add_argument("--configs", default="", help="comma-separated BASELINE config ids: run them all in ONE process group "
+                    "(one JSON line per config x mode; saves the spawn + NCCL bootstrap of separate launches)")
+    ap.add_argument("--modes", default="", help="with --configs: comma-separated modes (fwd,fwdbwd); default --mode")
+    a = ap.parse_args(argv)
     if a.config:
-        given = {x.split("=")[0].lstrip("-").replace("-", "_") for x in sys.argv[1:] if x.startswith("--")}
-        for key, val in presets[a.config].items():
+        given = {x.split("=")[0].lstrip("-").replace("-", "_") for x in argv if x.startswith("--")}
+        for key, val in PRESETS[a.config].items():
             if key not in given:
                 setattr(a, key, val)
     return a
@@ -147,28 +153,28 @@ class _HostCuda:
 
 
 def main():
-    a = parse()
+    a0 = parse()
     import torch
     import torch.distributed as dist
-    on_cpu = a.device == "cpu"
+    on_cpu = a0.device == "cpu"
     cu = _HostCuda if on_cpu else torch.cuda          # every CUDA runtime call below goes through `cu`
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus:
-        if world == 1 and a.gpus > 1:
+    if world != a0.gpus:
+        if world == 1 and a0.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1")
     cu.set_device(local_rank)
     dev = torch.device("cpu") if on_cpu else torch.device("cuda", local_rank)
 
-    if a.impl == "reference":
+    if a0.impl == "reference":
         ref_dir = os.path.join(ROOT, "baseline", "_ref")
         if not os.path.isdir(os.path.join(ref_dir, "yunchang")):
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/yunchang missing (pip install --target failed)"}))
             return
         sys.path.insert(0, ref_dir)
-    need_dist = world > 1 or a.impl == "reference"
+    need_dist = world > 1 or a0.impl == "reference"
     if need_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29533")
@@ -177,6 +183,28 @@ def main():
         else:
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
+    ctx = dict(torch=torch, dist=dist, on_cpu=on_cpu, cu=cu, world=world, rank=rank, local_rank=local_rank, dev=dev,
+               need_dist=need_dist)
+    runs = [a0]
+    if a0.configs:
+        base = [x for x in sys.argv[1:]]
+        modes = [m for m in (a0.modes.split(",") if a0.modes else [a0.mode]) if m]
+        runs = [parse(base + ["--config", c, "--mode", m]) for c in a0.configs.split(",") if c for m in modes]
+    bad = False
+    for a in runs:
+        ok = run_config(a, ctx)
+        bad = bad or ok is False
+    if need_dist:
+        dist.destroy_process_group()
+    if bad:
+        raise SystemExit(3)          # a wrong answer must not look like a benchmark result
+
+
+def run_config(a, ctx):
+    """One benchmark configuration inside an initialised process group; prints ONE JSON line on rank 0.
+    Returns False when the correctness check of our arm failed."""
+    torch, dist, on_cpu, cu = ctx["torch"], ctx["dist"], ctx["on_cpu"], ctx["cu"]
+    world, rank, local_rank, dev, need_dist = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["dev"], ctx["need_dist"]
     N = world
     U = min(a.ulysses, N)
     R = N // U
@@ -470,13 +498,14 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(n_launch * a.steps) if a.impl == "ours" else None,
             "comm": comm_probe,
+            "config_id": a.config or 3,
             "check": check,
             "staging": staging,
         }))
-    if need_dist:
-        dist.destroy_process_group()
+    del attn
     if a.impl == "ours" and check is not None and not check.get("ok", False):
-        raise SystemExit(3)          # a wrong answer must not look like a benchmark result
+        return False
+    return True
 
 
 if __name__ == "__main__":

@@ -52,3 +52,17 @@ def test_bench_two_ranks_all_phases(flags):
     comm = d["comm"]
     assert comm is not None and "error" not in comm, comm
     assert comm["compute_only_ms"] > 0 and "exposed_comm_ms" in comm
+
+
+def test_bench_multi_config_in_one_process_group():
+    """``--configs 2,3 --modes fwd,fwdbwd``: one JSON line per config x mode from ONE launch (the presets' shapes are
+    overridden by explicit flags, so the dry run stays tiny)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--device", "cpu", "--seq", "128", "--heads", "4", "--head-dim", "16", "--configs", "2,3", "--modes", "fwd,fwdbwd",
+           "--no-comm-probe"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert [(d["config_id"], d["config"]["mode"]) for d in lines] == [(2, "fwd"), (2, "fwdbwd"), (3, "fwd"), (3, "fwdbwd")]
+    assert lines[0]["config"]["parallelism"] == "ulysses2xring1" and lines[2]["config"]["parallelism"] == "ulysses1xring2"
