@@ -55,7 +55,7 @@ class AttnType(Enum):
 
 def flash_attn_forward_fp8(q, k, v, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1, -1), softcap=0.0,
                            alibi_slopes=None, return_softmax=False):
-    """Uniform-contract forward on block-scaled e4m3 operands (quantised on the fly).  EXPERIMENTAL."""
+    """Uniform-contract forward on block-scaled e4m3 operands (quantised on the fly): ``-> (out, lse)``."""
     from ..ops.attention import AttnParams
     from ..ops.fp8 import attn_fp8_fwd
     from ..parallel.layout import Seg
@@ -65,6 +65,8 @@ def flash_attn_forward_fp8(q, k, v, dropout_p=0.0, softmax_scale=None, causal=Fa
 
 
 _FOREIGN = {AttnType.AITER: "AMD ROCm (aiter)", AttnType.NPU: "Ascend NPU"}
+_QUANT_FWD = (AttnType.SAGE_AUTO, AttnType.SAGE_FP16, AttnType.SAGE_FP16_TRITON, AttnType.SAGE_FP8, AttnType.SAGE_FP8_SM90)
+_FP8_FWD = (AttnType.SAGE_AUTO, AttnType.SAGE_FP8, AttnType.SAGE_FP8_SM90)
 
 
 def is_torch_type(t) -> bool:
@@ -84,10 +86,29 @@ def select_flash_attn_impl(impl_type: AttnType, stage: str = "fwd-bwd", attn_pro
     if stage not in ("fwd-only", "bwd-only", "fwd-bwd"):
         raise ValueError(f"Unknown stage: {stage}")
     torch_like = is_torch_type(impl_type)
-    if impl_type in (AttnType.SAGE_FP8, AttnType.SAGE_FP8_SM90) and stage == "fwd-only":
+    if impl_type == AttnType.SPARSE_SAGE:
+        # the user's sparse-attention module is the kernel (reference :255-277); forward only, no LSE
+        if attn_processor is None or not callable(attn_processor):
+            raise ImportError("SparseSageAttention is only available with a sparse attention processor passed in")
+        if stage != "fwd-only":
+            raise ValueError(f"Unknown/Unsupported stage: {stage}")
+
+        def fn(q, k, v, causal=False, softmax_scale=None, *args, **kwargs):
+            return attn_processor(q, k, v, is_causal=causal, scale=softmax_scale, tensor_layout="NHD"), None
+
+        return fn
+    if impl_type in _QUANT_FWD:
+        # the reference's quantised family is forward-only third-party kernels (SageAttention int8/fp8, none of which
+        # has an sm_100 build).  B200-native equivalent: block-scaled e4m3 Q/K/V on tcgen05 kind::f8f6f4
+        # (ops/fp8.py).  SAGE_FP16 / SAGE_FP16_TRITON (int8 QK^T with a 16-bit PV product) run the 16-bit kernel:
+        # B200 has no int8 tensor-core path worth taking and 16-bit QK^T is the higher-precision superset.
         from ..ops import fp8
-        if fp8.enabled():            # experimental e4m3 block-scaled forward (forward-only, like the reference's SAGE_FP8)
-            return flash_attn_forward_fp8
+        from .attention import _func
+        if impl_type in _FP8_FWD and fp8.enabled():
+            if stage == "fwd-only":
+                return flash_attn_forward_fp8
+            if stage == "fwd-bwd":       # e4m3 forward, 16-bit backward on the saved operands
+                return lambda q, k, v, *a, **kw: _func("fp8", q, k, v, *a, **kw)
     if stage == "fwd-only":
         return pytorch_attn_forward if torch_like else flash_attn_forward
     if stage == "bwd-only":

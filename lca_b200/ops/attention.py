@@ -71,6 +71,8 @@ def block_is_visible(q_pos: PosSpec, k_pos: PosSpec, p: AttnParams) -> bool:
 
 
 def pick_engine(q: torch.Tensor, engine: Optional[str]) -> str:
+    if engine == "fp8":      # quantised forward (ops/fp8.py); everything it cannot take runs on the 16-bit engines
+        engine = None
     if engine in ("torch", "native"):
         if engine == "native" and not native.supports(q):
             raise RuntimeError(
@@ -110,7 +112,14 @@ def _dropout_args(p: AttnParams, B, H, qpt, kpt, q_grp, dropout_mask):
 
 def attn_block_fwd(q, k, v, q_pos: PosSpec, k_pos: PosSpec, p: AttnParams,
                    engine: Optional[str] = None, dropout_mask=None):
-    """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32."""
+    """-> out (B,Sq,H,D) q.dtype, lse (B,H,Sq) fp32.  ``engine="fp8"``: block-scaled e4m3 forward (``ops/fp8.py``:
+    tcgen05 ``kind::f8f6f4`` kernel on B200, bit-faithful PyTorch emulation elsewhere); the backward of such a
+    forward runs on the 16-bit engine against the saved 16-bit q/k/v (quantisation error is treated as noise, as in
+    FP8 training recipes that keep the backward of attention in bf16)."""
+    if engine == "fp8" and p.dropout_p == 0.0 and dropout_mask is None:
+        from . import fp8
+        if fp8.takes(q, k):
+            return fp8.attn_fp8_fwd(q, k, v, q_pos, k_pos, p)
     eng = pick_engine(q, engine)
     if eng == "native" and (p.dropout_p == 0.0 or (dropout_mask is None and native.dropout_supported(p))):
         return native.fmha_fwd(q, k, v, q_pos, k_pos, p)

@@ -507,8 +507,9 @@ static void fill_bwd_params(BwdParams& p, bool is_dkv, const at::Tensor& x0, con
   std::memset(&p, 0, sizeof(p));
   make_tmap(&p.tm_x0, x0, "x0", 128);
   make_tmap(&p.tm_x1, x1, "x1", 128);
-  make_tmap(&p.tm_y0, y0, "y0", 64);
-  make_tmap(&p.tm_y1, y1, "y1", 64);
+  p.y_rows = 64;                 // streamed rows per tile (both passes)
+  make_tmap(&p.tm_y0, y0, "y0", p.y_rows);
+  make_tmap(&p.tm_y1, y1, "y1", p.y_rows);
   p.n_xseg = static_cast<int>(xsegs.size());
   p.n_yseg = static_cast<int>(ysegs.size());
   int64_t tiles = 0;

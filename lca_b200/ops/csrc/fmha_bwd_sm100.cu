@@ -33,25 +33,38 @@ using namespace ptx;
 namespace {
 
 constexpr int BX = 128;   // stationary rows (TMEM lanes)
-constexpr int BY = 64;    // streamed rows per tile (TMEM columns of T0/T1)
 constexpr int kThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kTmaWarp = 9;
 
-template <int kD>
+// TMEM budget (512 columns).  dK/dV pass: two accumulators (2 x D) leave room for NS = 2 stages of (T0, T1);
+// dQ pass: one accumulator, so NS = 3 stages fit: the T GEMMs of tile j+2 are issued while tile j is still in the
+// element-wise stage and tile j+1 waits for it -- the tensor pipe no longer idles for a whole
+// "commit -> poll -> tcgen05.ld -> exp/dS -> tcgen05.st -> arrive -> poll" round trip per tile (measured r2 before the
+// change: tensor pipe 48 % active, issue slots 32 %, i.e. latency-bound, not throughput-bound).
+// dK/dV pass: two accumulators; at D = 128 only NS = 2 stages fit, at D = 64 three do.  (Measured and dropped in
+// round 2: 32-row streamed tiles with NS = 4 -- 5.56 ms against 3.62 ms at S = 32K, the per-tile cost does not shrink
+// with the tile, see profiles/r2/kernel_timings_r2.md.)
+template <int kD, bool kIsDKV, int kBY>
 struct Cfg {
+  static constexpr int BY = kBY;                          // streamed rows per tile (TMEM columns of T0/T1)
   static constexpr int DBLK = kD / 64;
   static constexpr int XBLK_BYTES = BX * 128;             // [128 rows][64 elem]
-  static constexpr int YBLK_BYTES = BY * 128;             // [64 rows][64 elem]
+  static constexpr int YBLK_BYTES = BY * 128;             // [BY rows][64 elem]
   static constexpr int XTILE_BYTES = DBLK * XBLK_BYTES;   // one stationary operand
   static constexpr int YTILE_BYTES = DBLK * YBLK_BYTES;   // one streamed operand
-  static constexpr int STAGES = 4;                        // streamed (Y0,Y1) tile pairs in flight
+  static constexpr int NACC = kIsDKV ? 2 : 1;              // accumulators of kD columns
+  static constexpr int NS_FIT = (512 - NACC * kD) / (2 * kBY);
+  static constexpr int NS = NS_FIT < 3 ? NS_FIT : 3;      // (T0, T1) stages in TMEM
+  static constexpr int STAGES = NS + 2;                   // streamed (Y0,Y1) tile pairs in flight (NS under MMA + loads)
   static constexpr int OFF_X = 0;
   static constexpr int OFF_Y = 2 * XTILE_BYTES;
-  static constexpr int OFF_STAT = OFF_Y + STAGES * 2 * YTILE_BYTES;   // per stage: lse2[64], delta[64]
-  static constexpr int OFF_BAR = OFF_STAT + STAGES * 2 * BY * 4;
+  static constexpr int OFF_STAT = OFF_Y + STAGES * 2 * YTILE_BYTES;   // dK/dV pass, per stage: lse2[64], delta[64]
+  static constexpr int OFF_BAR = OFF_STAT + (kIsDKV ? STAGES * 2 * BY * 4 : 0);
   static constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
-  static constexpr int TMEM_T0 = 0, TMEM_T1 = 128, TMEM_ACC0 = 256, TMEM_ACC1 = 256 + kD;
+  static constexpr int TMEM_T0 = 0, TMEM_T1 = NS * BY, TMEM_ACC0 = 2 * NS * BY, TMEM_ACC1 = TMEM_ACC0 + kD;
+  static_assert(TMEM_ACC0 + (kIsDKV ? 2 : 1) * kD <= 512, "TMEM columns");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
 struct Work {
@@ -88,8 +101,9 @@ __device__ __forceinline__ int sched_work(int round, int n_comm) {
   return round * G + c;
 }
 
-// streamed-tile enumeration: (inner head gi) x (segment) x (64-row tile), skipping tiles that are
+// streamed-tile enumeration: (inner head gi) x (segment) x (BY-row tile), skipping tiles that are
 // entirely masked for the stationary tile's position range.  Identical in every warp role.
+template <int BY>
 struct TileIter {
   int gi, seg, yt;
   int xmin, xmax, xgroup;
@@ -189,9 +203,11 @@ __device__ __forceinline__ void store_slice(void* base, int col0, const uint32_t
 //   tests/test_bwd_pipeline_model_cpu.py; reproduced on hardware in round 2: tools/gpu_repro_xfix.py hangs with the old
 //   rule, finishes with this one).  So every element-wise warp also arrives on x_empty (count 9) right after its
 //   x_full wait: X cannot be reloaded under a waiter.
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop, int kBY>
 __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_constant__ BwdParams p) {
-  using C = Cfg<kD>;
+  using C = Cfg<kD, kIsDKV, kBY>;
+  constexpr int NS = C::NS;
+  constexpr int BY = C::BY;
   constexpr bool kXf = !kIsDKV;       // see "x_empty protocol" above
   constexpr bool kPk = !kDrop;        // packed fp32x2 element-wise stage
   extern __shared__ uint8_t smem_raw[];
@@ -215,12 +231,13 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
   const uint32_t x_empty = a; a += 8;
   const uint32_t acc_full = a; a += 8;
   const uint32_t acc_empty = a; a += 8;
-  const uint32_t t_full = a; a += 16;      // [2]
-  const uint32_t p_full = a; a += 16;      // [2]
+  const uint32_t t_full = a; a += 8 * NS;
+  const uint32_t p_full = a; a += 8 * NS;
   const uint32_t y_full = a; a += 8 * C::STAGES;
   const uint32_t y_empty = a; a += 8 * C::STAGES;
   const uint32_t st_full = a; a += 8 * C::STAGES;
   const uint32_t st_empty = a; a += 8 * C::STAGES;
+  static_assert(32 + 16 * NS + 32 * C::STAGES <= 400, "barrier block overlaps the scheduler ring");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + C::OFF_BAR + 480);
   float* stat = reinterpret_cast<float*>(smem_gen + C::OFF_STAT);
   const uint32_t sc_full = smem + C::OFF_BAR + 400, sc_empty = smem + C::OFF_BAR + 416;   // dynamic scheduler ring
@@ -263,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     mbar_init(x_empty, kXf ? 9 : 1);
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 8);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(t_full + 8 * s, 1);
       mbar_init(p_full + 8 * s, 4);
     }
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           }
         }
         ++xc;
-        TileIter it;
+        TileIter<BY> it;
         it.init(p, wk);
         while (it.next(p)) {
           const int hy = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx / p.hx_per_hy;
@@ -325,23 +342,24 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             }
           }
           if constexpr (kIsDKV) {
+            // per-column statistics of the streamed query rows: asynchronous 4-byte copies global -> smem that arrive
+            // on st_full when they land (cp.async.mbarrier.arrive.noinc), so STAGES tiles of statistics are in flight.
+            // Round 2 finding: the synchronous ld.global -> st.shared -> arrive this replaces cost one global-load
+            // latency PER TILE on the producer's critical path and bounded the whole dK/dV pass (32-row tiles took
+            // as long per tile as 64-row tiles).  Invalid columns are zero-filled (their scores are masked anyway).
             __syncwarp();                      // lane 0 has acquired the arrival flag of this tile's rows
             mbar_wait(st_empty + 8 * st, par ^ 1);
             const float* l2 = p.lse2 + wk.b * p.stat_sb + hy * p.stat_sh;
             const float* dl = p.delta + wk.b * p.stat_sb + hy * p.stat_sh;
+            const uint32_t sdst = smem + C::OFF_STAT + st * 2 * BY * 4;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < BY / 32; ++i) {
               const int c = lane + 32 * i;
               const bool ok = c < it.nvalid;
-              if constexpr (kPk) {       // packed variant: statistics are staged negated (no negate modifiers on FFMA2/FADD2)
-                stat[st * 2 * BY + c] = ok ? -l2[it.y_row0 + c] : -INFINITY;
-                stat[st * 2 * BY + BY + c] = ok ? -dl[it.y_row0 + c] : 0.f;
-              } else {
-                stat[st * 2 * BY + c] = ok ? l2[it.y_row0 + c] : INFINITY;
-                stat[st * 2 * BY + BY + c] = ok ? dl[it.y_row0 + c] : 0.f;
-              }
+              cp_async_f32_zfill(sdst + c * 4, ok ? l2 + it.y_row0 + c : l2, ok);
+              cp_async_f32_zfill(sdst + (BY + c) * 4, ok ? dl + it.y_row0 + c : dl, ok);
             }
-            mbar_arrive(st_full + 8 * st);
+            cp_async_mbar_arrive_noinc(st_full + 8 * st);
           }
           ++yc;
         }
@@ -351,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       {
         constexpr uint32_t idesc_t = make_idesc_f16(kBf16 ? 1 : 0, BX, BY, 0, 0);
         constexpr uint32_t idesc_acc = make_idesc_f16(kBf16 ? 1 : 0, BX, kD, 0, 1);
-        uint32_t xc = 0, yc = 0, pc[2] = {0, 0}, ac = 0;
+        uint32_t xc = 0, yc = 0, ac = 0;
+        uint32_t g = 0;        // streamed tiles issued so far by this CTA: tile g lives in TMEM stage g % NS, phase g / NS
         auto issue_t = [&](uint32_t stage, int s) {
           const uint32_t x0 = smem + C::OFF_X, x1 = x0 + C::XTILE_BYTES;
           const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
@@ -386,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         for (int round = 0;; ++round) {
           Work wk;
           if (!decode_work(p, consumer_next(round), wk)) break;
-          TileIter it;
+          TileIter<BY> it;
           it.init(p, wk);
           mbar_wait(x_full, xc & 1);
           ++xc;
@@ -396,42 +415,42 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             continue;
           }
           tc_fence_after();
-          // prologue: T(0) and, if present, T(1)
-          uint32_t stage_q[2];
+          // prologue: the T GEMMs of the first NS tiles (as far as present)
+          // (the smem stage of streamed tile g is g % STAGES: yc == g when its T GEMMs are issued)
           int n_issued = 0;
           bool more = have;
-          for (int s = 0; s < 2 && more; ++s) {
+          const uint32_t g0 = g;
+          for (int i = 0; i < NS && more; ++i) {
             const uint32_t st = yc % C::STAGES;
+            const int s = static_cast<int>((g0 + i) % NS);
             mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
             ++yc;
             tc_fence_after();
             issue_t(st, s);
             mma_commit(t_full + 8 * s);
-            stage_q[s] = st;
             ++n_issued;
             more = it.next(p);
           }
           if (!more) mma_commit(x_empty);          // all T GEMMs (the only readers of X) are issued
-          for (int j = 0; j < n_issued; ++j) {
-            const int s = j & 1;
-            mbar_wait(p_full + 8 * s, pc[s] & 1);
-            ++pc[s];
+          for (int j = 0; j < n_issued; ++j, ++g) {
+            const int s = static_cast<int>(g % NS);
+            mbar_wait(p_full + 8 * s, (g / NS) & 1);
             if (j == 0) {
               mbar_wait(acc_empty, (ac & 1) ^ 1);
               ++ac;
             }
             tc_fence_after();
-            issue_acc(stage_q[s], s, j > 0);
-            mma_commit(y_empty + 8 * stage_q[s]);
-            if (more) {
+            const uint32_t sq = g % C::STAGES;
+            issue_acc(sq, s, j > 0);
+            mma_commit(y_empty + 8 * sq);
+            if (more) {                              // tile j + NS takes over the TMEM stage that was just consumed
               const uint32_t st = yc % C::STAGES;
               mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
               ++yc;
               tc_fence_after();
               issue_t(st, s);
               mma_commit(t_full + 8 * s);
-              stage_q[s] = st;
-              ++n_issued;
+                ++n_issued;
               more = it.next(p);
               if (!more) mma_commit(x_empty);
             }
@@ -442,13 +461,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     }
   } else {
     setmaxnreg_inc<200>();
-    // =========================================================== elementwise warpgroups (stage = wg)
+    // =========================================================== elementwise warpgroups
+    // streamed tile g (running count over the CTA's work items) sits in TMEM stage g % NS and belongs to warpgroup g % 2
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tT0_wg = tmem + lane_base + C::TMEM_T0 + wg * BY;
-    const uint32_t tT1_wg = tmem + lane_base + C::TMEM_T1 + wg * BY;
-    uint32_t tc = 0, yc = 0, afc = 0, xcw = 0;
+    uint32_t g = 0, yc = 0, afc = 0, xcw = 0;
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -470,21 +488,21 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           delta_r = p.delta[wk.b * p.stat_sb + wk.hx * p.stat_sh + wk.row0 + row];
         }
       }
-      TileIter it;
+      TileIter<BY> it;
       it.init(p, wk);
       int j = 0;
       while (it.next(p)) {
         const uint32_t st = yc % C::STAGES;
         const uint32_t ypar = (yc / C::STAGES) & 1;
         ++yc;
-        if ((j & 1) != wg) { ++j; continue; }                     // warpgroup wg owns the tiles with j % 2 == wg
-        const int sT = wg;                                        // TMEM stage of this tile
-        const uint32_t tT0 = tT0_wg, tT1 = tT1_wg;
-        constexpr int h_begin = 0, h_end = 2;                     // two 32-column halves per tile
+        const uint32_t gt = g++;
+        if (static_cast<int>(gt & 1u) != wg) { ++j; continue; }   // warpgroup wg owns the tiles with g % 2 == wg
+        const int sT = static_cast<int>(gt % NS);                 // TMEM stage of this tile
+        const uint32_t tT0 = tmem + lane_base + C::TMEM_T0 + sT * BY, tT1 = tmem + lane_base + C::TMEM_T1 + sT * BY;
+        constexpr int h_begin = 0, h_end = BY / 32;               // 32-column halves per tile
         const int hq = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx;     // query head (ALiBi slope index)
         const float slope = p.alibi ? p.alibi[wk.b * p.alibi_bstride + hq] : 0.f;
-        mbar_wait(t_full + 8 * wg, tc & 1);
-        ++tc;
+        mbar_wait(t_full + 8 * sT, (gt / NS) & 1);
         if constexpr (kIsDKV) mbar_wait(st_full + 8 * st, ypar);
         tc_fence_after();
         const int yb = it.ypos0 + (it.nvalid - 1) * p.y_pos_stride;
@@ -505,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int col = half * 32 + i;
-              const float dl = kIsDKV ? (kPk ? -st_dl[col] : st_dl[col]) : delta_r;
+              const float dl = kIsDKV ? st_dl[col] : delta_r;
               float x = __uint_as_float(t0[i]) * p.scale;
               float extra = 1.f;
               if (p.softcap > 0.f) {
@@ -525,19 +543,16 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           tmem_wait_st();
           mul = 1.f;
         }
+        // 16-column chunks, double buffered: the tcgen05.ld of chunk q+1 is in flight while chunk q is computed
+        // (before: load 2 x 32 columns -> wait -> compute -> store, twice per tile, i.e. two exposed TMEM round trips;
+        // the element-wise warpgroups, not the tensor pipe, bounded both passes: ~3000 clk per 64-column tile).
+        auto chunk = [&](int q, const uint32_t (&t0)[16], const uint32_t (&t1)[16], uint32_t* pp, uint32_t* ds) {
 #pragma unroll
-        for (int half = h_begin; half < h_end; ++half) {
-          uint32_t t0[32], t1[32];
-          tmem_ld32(tT0 + half * 32, t0);
-          tmem_ld32(tT1 + half * 32, t1);
-          tmem_wait_ld();
-          uint32_t pp[16], ds[16];
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
+          for (int c = 0; c < 16; c += 4) {
             float l2v[4], dlv[4];
             if constexpr (kIsDKV) {
-              const float4 a4 = *reinterpret_cast<const float4*>(st_l2 + half * 32 + c);
-              const float4 b4 = *reinterpret_cast<const float4*>(st_dl + half * 32 + c);
+              const float4 a4 = *reinterpret_cast<const float4*>(st_l2 + q * 16 + c);
+              const float4 b4 = *reinterpret_cast<const float4*>(st_dl + q * 16 + c);
               l2v[0] = a4.x; l2v[1] = a4.y; l2v[2] = a4.z; l2v[3] = a4.w;
               dlv[0] = b4.x; dlv[1] = b4.y; dlv[2] = b4.z; dlv[3] = b4.w;
             } else {
@@ -553,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
               float pd[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int col = half * 32 + c + e;
+                const int col = q * 16 + c + e;
                 const uint32_t ypos = static_cast<uint32_t>(it.ypos0 + col * p.y_pos_stride);
                 const uint32_t qp = kIsDKV ? ypos : static_cast<uint32_t>(xpos);
                 const uint32_t kp = kIsDKV ? static_cast<uint32_t>(xpos) : ypos;
@@ -569,20 +584,24 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
                 pv[0] = pd[0]; pv[1] = pd[1]; pv[2] = pd[2]; pv[3] = pd[3];
               }
             } else {
-              // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair
-              // l2v / dlv hold the NEGATED statistics in this variant: x = T0*mul + (-lse2), d = T1 + (-delta)
-              const uint64_t mul2 = ptx::pack_f32x2(mul, mul);
+              // packed fp32x2 arithmetic: one FFMA2 / FADD2 / FMUL2 per element pair (the packed forms take no negate
+              // modifier).  dQ pass: l2v / dlv are the row statistics negated once per work item:
+              //   x = T0*mul + (-lse2), d = T1 + (-delta), dS = P*d.
+              // dK/dV pass: l2v / dlv are the TRUE per-column statistics as the asynchronous copies delivered them:
+              //   y = T0*(-mul) + lse2 = -x (the negation folds into the MUFU operand), d' = T1*(-1) + delta = -d,
+              //   and P*d' = -dS goes to the dK GEMM; the epilogue multiplies dK by -scale.
+              const uint64_t mul2 = kIsDKV ? ptx::pack_f32x2(-mul, -mul) : ptx::pack_f32x2(mul, mul);
 #pragma unroll
               for (int e = 0; e < 4; e += 2) {
                 float x0, x1;
                 ptx::unpack_f32x2(ptx::fma_f32x2(
                     ptx::pack_f32x2(__uint_as_float(t0[c + e]), __uint_as_float(t0[c + e + 1])), mul2,
                     ptx::pack_f32x2(l2v[e], l2v[e + 1])), x0, x1);
-                pv[e] = ex2(x0);
-                pv[e + 1] = ex2(x1);
-                const uint64_t d = ptx::add_f32x2(
-                    ptx::pack_f32x2(__uint_as_float(t1[c + e]), __uint_as_float(t1[c + e + 1])),
-                    ptx::pack_f32x2(dlv[e], dlv[e + 1]));
+                pv[e] = ex2(kIsDKV ? -x0 : x0);
+                pv[e + 1] = ex2(kIsDKV ? -x1 : x1);
+                const uint64_t t1p = ptx::pack_f32x2(__uint_as_float(t1[c + e]), __uint_as_float(t1[c + e + 1]));
+                const uint64_t d = kIsDKV ? ptx::fma_f32x2(t1p, ptx::pack_f32x2(-1.f, -1.f), ptx::pack_f32x2(dlv[e], dlv[e + 1]))
+                                          : ptx::add_f32x2(t1p, ptx::pack_f32x2(dlv[e], dlv[e + 1]));
                 ptx::unpack_f32x2(ptx::mul_f32x2(ptx::pack_f32x2(pv[e], pv[e + 1]), d), dv[e], dv[e + 1]);
               }
             }
@@ -593,8 +612,26 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             ds[(c >> 1)] = pack2<kBf16>(dv[0], dv[1]);
             ds[(c >> 1) + 1] = pack2<kBf16>(dv[2], dv[3]);
           }
+        };
+        uint32_t ta0[16], ta1[16], tb0[16], tb1[16];
+        tmem_ld16(tT0, ta0);
+        tmem_ld16(tT1, ta1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int half = h_begin; half < h_end; ++half) {
+          uint32_t pp[16], ds[16];
+          tmem_ld16(tT0 + half * 32 + 16, tb0);
+          tmem_ld16(tT1 + half * 32 + 16, tb1);
+          chunk(2 * half, ta0, ta1, pp, ds);
+          tmem_wait_ld();
+          if (half + 1 < h_end) {
+            tmem_ld16(tT0 + (half + 1) * 32, ta0);
+            tmem_ld16(tT1 + (half + 1) * 32, ta1);
+          }
+          chunk(2 * half + 1, tb0, tb1, pp + 8, ds + 8);
           if constexpr (kIsDKV) tmem_st16(tT0 + half * 16, pp);
           tmem_st16(tT1 + half * 16, ds);
+          if (half + 1 < h_end) tmem_wait_ld();
         }
         tmem_wait_st();
         tc_fence_before();
@@ -624,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           tacc = tmem + lane_base + (wg == 0 ? C::TMEM_ACC0 : C::TMEM_ACC1);
           void* ob = wg == 0 ? (xs.o_base0 ? xs.o_base0 : p.out0) : (xs.o_base1 ? xs.o_base1 : p.out1);
           obase = reinterpret_cast<uint8_t*>(ob);
-          mul = wg == 0 ? p.scale : 1.f;
+          mul = wg == 0 ? (kPk ? -p.scale : p.scale) : 1.f;     // packed dK/dV pass accumulates -dS (see above)
         } else {
           ncols = kD / 2; col_begin = wg * (kD / 2);
           tacc = tmem + lane_base + C::TMEM_ACC0;
@@ -670,10 +707,10 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop = false>
+template <int kD, bool kBf16, bool kIsDKV, bool kDyn, bool kDrop = false, int kBY = 64>
 static cudaError_t launch_impl(const BwdParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<kD>;
-  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kDrop>;
+  using C = Cfg<kD, kIsDKV, kBY>;
+  auto kern = fmha_bwd_kernel<kD, kBf16, kIsDKV, kDyn, kDrop, kBY>;
   // fused launches: the push CTAs stage their bulk copies in the same dynamic shared memory (usp_comm.cuh)
   constexpr int kSmem = C::SMEM_BYTES > kPushSmemBytes ? C::SMEM_BYTES : kPushSmemBytes;
   static bool configured = false;

@@ -136,7 +136,8 @@ struct XSegD {
 //   dKV pass: X = (K, V)   [Hx = Hkv], Y = (Q, dO) [Hy = H],   n_inner = H/Hkv (query heads per KV head)
 struct BwdParams {
   CUtensorMap tm_x0, tm_x1;           // box (64,1,128,1)
-  CUtensorMap tm_y0, tm_y1;           // box (64,1,64,1)
+  CUtensorMap tm_y0, tm_y1;           // box (64,1,y_rows,1)
+  int y_rows;                         // streamed rows per tile (64)
   int n_xseg, n_yseg;
   XSegD xseg[kMaxSeg];
   KSegD yseg[kMaxSeg];

@@ -1,4 +1,4 @@
-"""Block-scaled FP8 (e4m3) attention forward -- EXPERIMENTAL.
+"""Block-scaled FP8 (e4m3) attention forward.
 
 Role: the reference reaches fp8 only through third-party forward-only kernels (``AttnType.SAGE_FP8*``,
 ``kernels/__init__.py:177-254``; FA3 with caller-supplied fp8 tensors, ``kernels/attention.py:258-292``), none of
@@ -6,10 +6,12 @@ which run on sm_100.  Here: Q and K are quantised to e4m3 with one fp32 scale pe
 with one scale per (batch, kv head); the tcgen05 ``kind::f8f6f4`` kernel (``csrc/fmha_fwd_fp8_sm100.cu``) folds the
 Q/K block scales into the softmax argument and the V scale into the final normalisation.
 
-Status: the CUDA path is compile-checked only (this round's GPU budget was spent before it could be validated),
-so it is opt-in: ``LCA_B200_EXPERIMENTAL_FP8=1``.  :func:`attn_fp8_emulated` is the bit-faithful PyTorch model of
-the kernel's arithmetic (quantise -> fp32 matmuls -> e4m3 P) used as its oracle and as the CPU path.
-Forward only, like the reference's fp8 paths.
+Status: validated on B200 in round 2 (``tests/test_fp8.py`` against :func:`attn_fp8_emulated`, the bit-faithful
+PyTorch model of the kernel's arithmetic: quantise -> fp32 matmuls -> e4m3 P; timings and errors in
+``profiles/r2/``).  Selected by ``AttnType.SAGE_FP8 / SAGE_FP8_SM90 / SAGE_AUTO`` (the reference's quantised
+forward-only family) through the ``"fp8"`` engine of :func:`lca_b200.ops.attention.attn_block_fwd`; ``LCA_B200_FP8=0``
+sends those types to the bf16 kernel instead.  Forward only, like the reference's fp8 paths: under autograd the
+backward runs in 16 bit on the saved 16-bit operands.
 """
 from __future__ import annotations
 
@@ -28,7 +30,16 @@ BLOCK = 128
 
 
 def enabled() -> bool:
-    return os.environ.get("LCA_B200_EXPERIMENTAL_FP8", "0") == "1"
+    """The CUDA fp8 kernel may be used (``LCA_B200_FP8=0`` / legacy ``LCA_B200_EXPERIMENTAL_FP8=0`` turn it off)."""
+    return os.environ.get("LCA_B200_FP8", os.environ.get("LCA_B200_EXPERIMENTAL_FP8", "1")) == "1"
+
+
+def takes(q: torch.Tensor, k: torch.Tensor) -> bool:
+    """Inputs the fp8 forward handles: the CUDA kernel needs head_dim 128 and 16-bit inputs; the emulation (CPU, other
+    head dims) is O(Sq*Sk) memory and only meant for tests, so it is limited to small blocks."""
+    if q.is_cuda and native.available():
+        return enabled() and q.shape[-1] == 128 and q.dtype in (torch.bfloat16, torch.float16)
+    return enabled() and q.shape[1] * k.shape[1] <= 4096 * 4096
 
 
 def quantize_blockwise(x: torch.Tensor, per_head: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -73,7 +73,14 @@ def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dro
     (``pg`` = the sequence process group) or "ring" (``pg`` = a ring group; ``cu_seqlens`` = cumulative LOCAL lengths
     of a packed variable-length shard).  Returns ``None`` when the caller has to take the collective path, else the
     output (``return_lse``: ``(out, lse (B, H, rows))``)."""
-    if backend == "collective" or getattr(attn_type, "value", "").startswith("torch"):
+    tag = getattr(attn_type, "value", "")
+    if backend == "collective" or tag.startswith("torch"):
+        return None
+    if tag in ("sage_fp8", "sage_fp8_sm90", "sage_auto", "sparse_sage"):
+        # quantised / user-supplied forward kernels run per ring block on the collective path (as in the reference,
+        # where SAGE_* only exist as "fwd-only" block kernels inside the ring loop): the push CTAs are part of the
+        # 16-bit kernels
+        _note_once(("attn_type", tag), f"AttnType {tag}: collective path (per-block forward kernel)")
         return None
     if not q.is_cuda:
         return None
@@ -108,7 +115,8 @@ def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dro
         _note_once(("shape", tuple(q.shape), tuple(k.shape)), f"fused backend skipped for q {tuple(q.shape)} k {tuple(k.shape)}")
         return None
     need_bwd = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
-    if not eng.reserve(q, k, need_bwd):
+    kv_chunk = eng.reserve(q, k, need_bwd)
+    if not kv_chunk:
         if strict:
             raise RuntimeError("fused backend: the symmetric slab does not fit (LCA_B200_SLAB_MAX_GB / free memory)")
         _note_once(("slab", tuple(q.shape)), f"fused backend skipped: staging slab for q {tuple(q.shape)} does not fit; "
@@ -117,4 +125,4 @@ def try_fused(kind: str, pg, backend: str, attn_type, q, k, v, variant: str, dro
     seed = eng.dropout_seed() if dropout_p > 0.0 else 0
     with nvtx_range(f"lca.fused.{kind}.{variant}"):
         return eng.attention(q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
-                             dropout_p, seed, cu_seqlens, return_lse)
+                             dropout_p, seed, cu_seqlens, return_lse, kv_chunk)

@@ -89,8 +89,8 @@ class _Slab:
 
     def close(self):
         C = native.ext()
-        for i, p in enumerate(self.peer_ptrs or []):
-            if i != self._me:
+        for p in (self.peer_ptrs or []):
+            if p != self.ptr:
                 C.symm_unmap(p)
         C.symm_free(self.ptr)
 
@@ -154,10 +154,16 @@ def _make_slab(nbytes: int, group, device: torch.device):
 
 
 class FusedUSPEngine:
-    def __init__(self, sp_group, U: int, R: int, u: int, r: int, device: torch.device):
+    def __init__(self, sp_group, U: int, R: int, u: int, r: int, device: torch.device, ulysses_low: bool = True):
         self.group, self.U, self.R, self.u, self.r = sp_group, U, R, u, r
         self.P = U * R
-        self.me = r * U + u                     # index inside the sp group (ulysses-low ordering)
+        # LOGICAL sp index used by the kernels and every segment list: ring-major, ``d = r * U + u``.  With
+        # ``use_ulysses_low=False`` (``globals.py:59-78`` of the reference: ring groups on the contiguous ranks) the
+        # rank inside ``sp_group`` is ``u * R + r`` instead; only the peer-pointer tables are permuted (logical ->
+        # group rank), so the kernels never see the difference.
+        self.me = r * U + u
+        self.ulysses_low = bool(ulysses_low)
+        self.group_rank_of = [d if ulysses_low else (d % U) * R + d // U for d in range(self.P)]
         self.device = device
         self.slab: Optional[_Slab] = None
         self.sig: Optional[_Slab] = None
@@ -169,11 +175,18 @@ class FusedUSPEngine:
         # direction (~750 GB/s) needs >= 12; with the dynamic scheduler they join the compute pool afterwards (measured
         # N=2: 8 -> 16 CTAs: forward 2064 -> 2098 TFLOPS, Ulysses S=32K forward 5.8 -> 5.1 ms)
         self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "16"))
-        self._refused = set()                   # call shapes whose slab did not fit (decided collectively, once)
+        self._plan = {}                         # call shape -> kv heads per launch (0 = refused), decided collectively, once
         self.slab_bytes = 0
         self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
-        self.sig = _make_slab(SIG_BYTES, sp_group, device)
+        self.sig = self._logical(_make_slab(SIG_BYTES, sp_group, device))
+
+    def _logical(self, slab):
+        """Re-index a freshly exchanged slab's peer pointers by logical sp index (identity for ulysses-low meshes)."""
+        slab.peer_ptrs = [slab.peer_ptrs[g] for g in self.group_rank_of]
+        if slab.peer_ptrs[self.me] != slab.ptr:
+            raise RuntimeError("fused engine: mesh coordinates do not match the rank inside the sp group")
+        return slab
 
     def close(self) -> None:
         """Release the slabs (collective: peers must have stopped writing)."""
@@ -230,23 +243,53 @@ class FusedUSPEngine:
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         return bool(int(t.item()))
 
-    def reserve(self, q, k, need_bwd: bool) -> bool:
-        """Make sure the slab can hold this call (collective only when it has to grow).  Returns False -- on EVERY
-        rank -- when the slab would exceed ``LCA_B200_SLAB_MAX_GB`` (default: 60 % of the memory that is free right
-        now) or cannot be allocated; the caller then uses the collective backend, whose memory is O(S/P)."""
+    def _cap_bytes(self) -> int:
+        """Upper bound for the data slab: ``LCA_B200_SLAB_MAX_GB``, else 60 % of the memory that is free right now
+        (counting the slab we already hold)."""
+        have = self.slab.nbytes if self.slab is not None else 0
+        cap_gb = float(os.environ.get("LCA_B200_SLAB_MAX_GB", "0") or 0)
+        if cap_gb > 0:
+            return int(cap_gb * 2**30)
+        return int(0.6 * (torch.cuda.mem_get_info(self.device)[0] + have))
+
+    def reserve(self, q, k, need_bwd: bool) -> int:
+        """Make sure the slab can hold this call (collective only for a call shape seen for the first time or when the
+        slab has to grow).  Returns the number of KV HEADS PER FUSED LAUNCH: ``Hkv`` = the whole call in one launch;
+        a smaller divisor = the call is executed as ``Hkv / c`` launches over head groups, so the staging is
+        O(S * c * D) instead of O(S * Hkv * D) (bounded staging: the all-gather data model of the fused kernels keeps
+        the K/V (and, for the backward, Q/dO) of every rank for the heads of ONE launch; looping over head groups is
+        what keeps that under the cap at long sequence lengths); 0 -- on EVERY rank -- when not even the smallest head
+        group fits or the slab cannot be allocated: the caller then uses the collective backend (O(S/P) memory).
+        ``LCA_B200_HEAD_CHUNK=<kv heads>`` forces a group size (tests, memory-constrained jobs)."""
         B, rows, H, D = q.shape
+        Hkv = k.shape[2]
         bwd = bool(need_bwd and self.with_bwd)
-        key = (B, rows, H, k.shape[2], D, q.element_size(), bwd)
-        if key == self.key:
-            return True
-        if key in self._refused:
-            return False
-        try:
-            self._ensure(*key)
-            return True
-        except _SlabDoesNotFit:
-            self._refused.add(key)
-            return False
+        key = (B, rows, H, Hkv, D, q.element_size(), bwd)
+        if key in self._plan:
+            return self._plan[key]
+        c = self._plan_heads(*key)
+        if c:
+            try:
+                self._ensure(B, rows, H // Hkv * c, c, D, q.element_size(), bwd)
+            except _SlabDoesNotFit:
+                c = 0
+        self._plan[key] = c
+        if 0 < c < Hkv:
+            _LOG.info("fused engine %dx%d: q %s runs as %d launches of %d kv heads (slab %.2f GiB)", self.U, self.R,
+                      tuple(q.shape), Hkv // c, c, self.slab_bytes / 2**30)
+        return c
+
+    def _plan_heads(self, B, rows, H, Hkv, D, esz, bwd: bool) -> int:
+        cands = head_chunk_candidates(Hkv, self.U)
+        forced = int(os.environ.get("LCA_B200_HEAD_CHUNK", "0") or 0)
+        if forced in cands:
+            cands = [forced]
+        g = H // Hkv
+        cap = self._cap_bytes()
+        mine = next((c for c in cands if self._layout(B, rows, g * c, c, D, esz, bwd)[1] <= cap), 0)
+        t = torch.tensor([mine], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)      # every rank must take the same plan
+        return int(t.item())
 
     def _ensure(self, B, rows, H, Hkv, D, esz, bwd: bool = True):
         key = (B, rows, H, Hkv, D, esz, bwd)
@@ -254,10 +297,7 @@ class FusedUSPEngine:
             return
         offs, total = self._layout(B, rows, H, Hkv, D, esz, bwd)
         if self.slab is None or self.slab.nbytes < total:
-            have = self.slab.nbytes if self.slab is not None else 0
-            cap_gb = float(os.environ.get("LCA_B200_SLAB_MAX_GB", "0") or 0)
-            free = torch.cuda.mem_get_info(self.device)[0] + have
-            cap = int(cap_gb * 2**30) if cap_gb > 0 else int(0.6 * free)
+            cap = self._cap_bytes()
             if not self._agree(total <= cap):
                 raise _SlabDoesNotFit(f"slab of {total / 2**30:.2f} GiB exceeds the cap ({cap / 2**30:.2f} GiB)")
             if self.slab is not None:
@@ -278,7 +318,7 @@ class FusedUSPEngine:
                 if new is not None:
                     new.free_local()
                 raise _SlabDoesNotFit(f"could not allocate a {total / 2**30:.2f} GiB symmetric slab on every rank")
-            self.slab = new.exchange(self.group)
+            self.slab = self._logical(new.exchange(self.group))
             _LOG.info("fused engine %dx%d: slab %.2f GiB (%s)", self.U, self.R, total / 2**30,
                       "fwd+bwd staging" if bwd else "fwd staging")
         self.off_q, self.off_k, self.off_v, self.off_o = offs["q"], offs["k"], offs["v"], offs["o"]
@@ -568,14 +608,29 @@ class FusedUSPEngine:
 
     # ------------------------------------------------------------------------------ autograd entry
     def attention(self, q, k, v, variant, softmax_scale, causal, window_size, softcap, alibi_slopes, deterministic,
-                  dropout_p: float = 0.0, dropout_seed: int = 0, cu_seqlens=None, return_lse: bool = False):
-        p = AttnParams.make(q, softmax_scale, causal, window_size, softcap, alibi_slopes, dropout_p, deterministic)
-        if p.dropout_p > 0.0:        # EXPERIMENTAL (native.dropout_supported): the mask needs no communication at all
-            from dataclasses import replace
-            p = replace(p, dropout_seed=int(dropout_seed))
+                  dropout_p: float = 0.0, dropout_seed: int = 0, cu_seqlens=None, return_lse: bool = False,
+                  kv_heads_per_launch: int = 0):
+        from dataclasses import replace
         cu = None if cu_seqlens is None else tuple(int(x) for x in cu_seqlens)
-        out, lse = _FusedAttnFunc.apply(q, k, v, self, canonical_variant(variant), p, cu)
-        return (out, lse) if return_lse else out
+        H, Hkv = q.shape[2], k.shape[2]
+        c = kv_heads_per_launch if 0 < kv_heads_per_launch < Hkv else Hkv
+        g = H // Hkv
+        outs, lses = [], []
+        for h0 in range(0, Hkv, c):          # one launch per head group (a single iteration unless the slab is capped)
+            whole = c == Hkv
+            qs = q if whole else q[:, :, h0 * g:(h0 + c) * g]
+            ks, vs = (k, v) if whole else (k[:, :, h0:h0 + c], v[:, :, h0:h0 + c])
+            al = alibi_slopes if (whole or alibi_slopes is None) else alibi_slopes[..., h0 * g:(h0 + c) * g]
+            p = AttnParams.make(qs, softmax_scale, causal, window_size, softcap, al, dropout_p, deterministic)
+            if p.dropout_p > 0.0:    # the mask needs no communication: it is a function of global coordinates
+                p = replace(p, dropout_seed=int(dropout_seed), head_offset=h0 * g)
+            o, l = _FusedAttnFunc.apply(qs, ks, vs, self, canonical_variant(variant), p, cu)
+            outs.append(o)
+            lses.append(l)
+        out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=2)
+        if not return_lse:
+            return out
+        return out, (lses[0] if len(lses) == 1 else torch.cat(lses, dim=1))
 
     def _arm_dropout(self, p: AttnParams, Hl: int) -> None:
         """Hand the dropout key to the NEXT fused launch: local query head h of this rank is global head u*Hl + h."""
@@ -583,6 +638,14 @@ class FusedUSPEngine:
             from ..ops import dropout as _d
             native.ext().set_next_dropout([_d.p8_of(p.dropout_p), int(p.dropout_seed) & 0xFFFFFFFF,
                                            self.u * Hl + int(p.head_offset)])
+
+
+def head_chunk_candidates(Hkv: int, U: int):
+    """KV-head group sizes a call may be split into, largest first: divisors of ``Hkv`` that keep every group
+    divisible by the Ulysses degree (replicated kv heads, ``Hkv < U``, are never split)."""
+    if Hkv % U:
+        return [Hkv]
+    return [c for c in range(Hkv, 0, -1) if Hkv % c == 0 and c % U == 0]
 
 
 def _dense_heads(t: torch.Tensor) -> torch.Tensor:
@@ -686,17 +749,13 @@ def engine_for_mesh(pgs, q, strict: bool = False):
         return None
     key = ("mesh", id(pgs.SP_PG), q.device.index)
     if key not in _ENGINES:
-        if not mesh.use_ulysses_low:
-            if strict:
-                raise RuntimeError("fused backend requires use_ulysses_low=True")
-            _ENGINES[key] = None
-        elif not _same_node_p2p(pgs.SP_PG, q.device):
+        if not _same_node_p2p(pgs.SP_PG, q.device):
             if strict:
                 raise RuntimeError("fused backend needs all SP ranks on one node with P2P access")
             _ENGINES[key] = None
         else:
             eng = FusedUSPEngine(pgs.SP_PG, mesh.ulysses_degree, mesh.ring_degree, mesh.ulysses_rank, mesh.ring_rank,
-                                 q.device)
+                                 q.device, ulysses_low=mesh.use_ulysses_low)
             eng.ulysses_pg, eng.ring_pg = pgs.ULYSSES_PG, pgs.RING_PG
             _ENGINES[key] = eng
     return _ENGINES[key]

@@ -35,6 +35,8 @@ def _engine_for(attn_type) -> Optional[str]:
     name = getattr(attn_type, "value", attn_type)
     if isinstance(name, str) and name.startswith("torch"):
         return "torch"
+    if name in ("sage_fp8", "sage_fp8_sm90", "sage_auto"):      # the quantised forward family -> e4m3 tcgen05 forward
+        return "fp8"
     return None
 
 
@@ -169,6 +171,19 @@ class RingAttnFunc(torch.autograd.Function):
         return (dq, dk, dv) + (None,) * 14
 
 
+def _processor_attention(attn_processor, group, q, k, v, softmax_scale, causal, return_attn_probs):
+    """``AttnType.SPARSE_SAGE``: the user's sparse-attention module IS the block kernel (reference
+    ``kernels/__init__.py:255-277``: ``attn_processor(q, k, v, is_causal=, scale=, tensor_layout="NHD")`` -> out, no
+    LSE).  Without an LSE partial results cannot be merged, hence ring degree 1 only (reference guard
+    ``hybrid/attn_layer.py:51-54``); Ulysses parallelism composes freely (heads are independent)."""
+    if attn_processor is None or not callable(attn_processor):
+        raise ImportError("AttnType.SPARSE_SAGE needs a sparse attention processor module passed as attn_processor")
+    if group_size(group) > 1:
+        raise RuntimeError("Sparse Sage attention does not support ring degree > 1.")
+    out = attn_processor(q, k, v, is_causal=causal, scale=softmax_scale, tensor_layout="NHD")
+    return (out, None, None) if return_attn_probs else out
+
+
 def _make_funcs(variant: str):
     variant = canonical_variant(variant)
 
@@ -178,6 +193,8 @@ def _make_funcs(variant: str):
         """``backend``: "auto" (default, ``LCA_B200_BACKEND``) runs the ring on the fused NVLink engine when the group
         is P2P-reachable on one node (push CTAs + tcgen05 attention in one kernel per rank), else -- and always with
         "collective" -- the NCCL/gloo P2P ring below."""
+        if getattr(attn_type, "value", attn_type) == "sparse_sage":
+            return _processor_attention(attn_processor, group, q, k, v, softmax_scale, causal, return_attn_probs)
         if head_offset == 0 and dropout_seed is None:
             from .fused import resolve_backend, try_fused
             res = try_fused("ring", group, resolve_backend(backend), attn_type, q, k, v, variant, dropout_p, softmax_scale,

@@ -36,6 +36,7 @@ def _dense_case(rank, world, c):
     kw = dict(c.get("kw", {}))
     H, Hkv, S, D, B = c["H"], c["Hkv"], c["S"], c["D"], c.get("B", 1)
     module = c.get("module", "hybrid")
+    low = c.get("ulysses_low", True)
     dev = torch.device("cuda", rank)
     g = torch.Generator().manual_seed(11)
     q = torch.randn(B, S, H, D, generator=g).to(dev, torch.bfloat16)
@@ -50,9 +51,9 @@ def _dense_case(rank, world, c):
         torch.manual_seed(777)                   # the oracle draws its dropout seed from torch's CPU generator
     ref = pytorch_attn_func(q1, k1, v1, **kw)
     ref.backward(do)
-    set_seq_parallel_pg(U, R, rank, world)
+    set_seq_parallel_pg(U, R, rank, world, use_ulysses_low=low)
     key = _key(variant)
-    sh = lambda t: EXTRACT_FUNC_DICT[key](t, rank, world, rd=R, ud=U).detach().clone()
+    sh = lambda t: EXTRACT_FUNC_DICT[key](t, rank, world, rd=R, ud=U, use_ulysses_low=low).detach().clone()
     lq, lk, lv = (sh(t).requires_grad_() for t in (q, k, v))
     if module == "ulysses":
         attn = UlyssesAttention(None, backend="fused")
@@ -171,6 +172,9 @@ def _matrix_worker(rank, world, cases):
     failures = []
     for c in cases:
         name = c["name"]
+        env = c.get("env", {})
+        saved = {k_: os.environ.get(k_) for k_ in env}
+        os.environ.update(env)
         try:
             _RUNNERS[c.get("kind", "dense")](rank, world, dict(c))
             if rank == 0:
@@ -179,6 +183,12 @@ def _matrix_worker(rank, world, cases):
             # numerical mismatch: every rank finished the case's collectives, so the matrix can go on
             failures.append((name, traceback.format_exc(limit=3)))
             print(f"[matrix n={world}] FAIL {name} (rank {rank})", flush=True)
+        finally:
+            for k_, v_ in saved.items():
+                if v_ is None:
+                    os.environ.pop(k_, None)
+                else:
+                    os.environ[k_] = v_
     assert not failures, "\n".join(f"--- {n}\n{tb}" for n, tb in failures)
 
 
@@ -204,6 +214,11 @@ CASES = {
         C("r2_zigzag_alibi", 1, 2, "zigzag", 4, 4, 1024, 128, dict(causal=True, alibi_slopes="auto")),
         dict(name="r2_varlen_basic", kind="varlen", variant="basic", lens=[512, 1024, 256, 2048], H=4, Hkv=2, D=128),
         dict(name="r2_varlen_zigzag", kind="varlen", variant="zigzag", lens=[512, 1024, 256, 2048], H=4, Hkv=2, D=128),
+        # bounded staging: the call runs as one fused launch per kv-head group (forward, backward, dropout head keys, ALiBi)
+        C("r2_zigzag_headgroups", 1, 2, "zigzag", 8, 4, 1024, 128, dict(causal=True, alibi_slopes="auto"),
+          env={"LCA_B200_HEAD_CHUNK": "1"}),
+        C("u2_headgroups_dropout", 2, 1, "basic", 8, 4, 1024, 128, dict(causal=True, dropout_p=0.2),
+          env={"LCA_B200_HEAD_CHUNK": "2"}),
         C("r2_zigzag_128k", 1, 2, "zigzag", 2, 1, 131072, 128, kind="long"),
     ],
     4: [
@@ -213,6 +228,9 @@ CASES = {
         C("u2r2_stripe_d64", 2, 2, "stripe", 4, 4, 2048, 64),
         C("u4_mqa", 4, 1, "basic", 8, 2, 2048, 128),
         C("u2r2_batch2", 2, 2, "zigzag", 4, 2, 2048, 128, B=2),
+        # use_ulysses_low=False: ring groups on the contiguous ranks (reference globals.py:59-78)
+        C("u2r2_ulysses_high", 2, 2, "zigzag", 4, 2, 2048, 128, ulysses_low=False),
+        C("u2r2_ulysses_high_headgroups", 2, 2, "zigzag", 8, 4, 2048, 128, ulysses_low=False, env={"LCA_B200_HEAD_CHUNK": "2"}),
         dict(name="r4_varlen_zigzag", kind="varlen", variant="zigzag", lens=[1024, 2048, 512, 4096], H=4, Hkv=2, D=128),
         C("r4_zigzag_128k", 1, 4, "zigzag", 2, 1, 131072, 128, kind="long"),
     ],
@@ -224,6 +242,7 @@ CASES = {
         C("u2r4_stripe", 2, 4, "stripe", 4, 4, 8192, 128),
         C("u8_mqa", 8, 1, "basic", 16, 2, 8192, 128),
         C("u2r4_batch2", 2, 4, "zigzag", 8, 4, 4096, 128, B=2),
+        C("u4r2_ulysses_high", 4, 2, "zigzag", 16, 8, 8192, 128, ulysses_low=False),
         C("r8_zigzag_256k", 1, 8, "zigzag", 2, 1, 262144, 128, kind="long"),
     ],
 }

@@ -226,3 +226,42 @@ def test_varlen_segments_describe_packed_sequences(R, variant):
             out[:, qm] = o
         want = torch.cat([refs[i][:, loc_idx[r][i]] for i in range(len(glens))], dim=1)
         torch.testing.assert_close(out, want, atol=1e-5, rtol=1e-5)
+
+
+def test_head_group_candidates_keep_ulysses_and_gqa_divisibility():
+    from lca_b200.parallel.fused_engine import head_chunk_candidates
+    assert head_chunk_candidates(8, 1) == [8, 4, 2, 1]
+    assert head_chunk_candidates(8, 2) == [8, 4, 2]
+    assert head_chunk_candidates(8, 8) == [8]
+    assert head_chunk_candidates(2, 8) == [2]            # replicated kv heads are never split
+    assert head_chunk_candidates(12, 4) == [12, 4]
+    for Hkv in range(1, 17):
+        for U in (1, 2, 4, 8):
+            for c in head_chunk_candidates(Hkv, U):
+                assert Hkv % c == 0 and (c % U == 0 or Hkv % U != 0)
+
+
+@pytest.mark.parametrize("U,R", [(2, 2), (4, 2), (2, 4), (1, 8), (8, 1)])
+def test_staging_shrinks_with_the_head_group(U, R):
+    """Bounded staging: the slab of a launch over c kv heads is ~c/Hkv of the whole call's slab."""
+    e = _engine(U, R, 0, 0)
+    B, rows, D, esz = 1, 4096, 128, 2
+    Hkv, g = 8, 4
+    from lca_b200.parallel.fused_engine import head_chunk_candidates
+    full = e.staging_bytes(B, rows, g * Hkv, Hkv, D, esz, True)
+    for c in head_chunk_candidates(Hkv, U):
+        part = e.staging_bytes(B, rows, g * c, c, D, esz, True)
+        assert part <= full * c / Hkv * 1.02 + 64 * 1024
+
+
+@pytest.mark.parametrize("U,R", [(2, 2), (4, 2), (2, 4)])
+def test_ulysses_high_mesh_permutes_only_the_pointer_tables(U, R):
+    """use_ulysses_low=False: logical index d = r*U + u maps to group rank u*R + r (a permutation; identity otherwise)."""
+    from lca_b200.parallel.mesh import coords_to_rank
+    P = U * R
+    for low in (True, False):
+        table = [d if low else (d % U) * R + d // U for d in range(P)]
+        assert sorted(table) == list(range(P))
+        for r in range(R):
+            for u in range(U):
+                assert table[r * U + u] == coords_to_rank(u, r, 0, U, R, low)
