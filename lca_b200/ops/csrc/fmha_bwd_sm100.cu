@@ -103,37 +103,65 @@ __device__ __forceinline__ int sched_work(int round, int n_comm) {
 
 // streamed-tile enumeration: (inner head gi) x (segment) x (BY-row tile), skipping tiles that are
 // entirely masked for the stationary tile's position range.  Identical in every warp role.
+// Positions grow with the tile index inside a segment, so the visible tiles of a segment are ONE contiguous range
+// [lo, hi): it is computed when the iterator enters a segment (two integer divisions, rare); the per-tile step is a
+// compare and three multiply-adds.  Round-2 profile: the single-thread roles (MMA issuer, TMA producer) -- not the
+// tensor pipe, not the element-wise warpgroups -- bounded all three kernels, and the per-tile window tests + the
+// constant-bank reload of the segment record were a third of their instruction stream
+// (tests/test_properties_cpu.py checks the range form against the per-tile tests it replaces).
 template <int BY>
 struct TileIter {
-  int gi, seg, yt;
+  int gi, seg, yt, yt_end;
   int xmin, xmax, xgroup;
+  int s_row0, s_nrows, s_pos0, s_flag;    // current segment (cached)
   int y_row0, nvalid, ypos0, flag;
   __device__ __forceinline__ void init(const BwdParams& p, const Work& wk) {
-    gi = 0; seg = 0; yt = -1;
+    gi = 0; seg = -1; yt = 0; yt_end = 0;
     xmin = wk.pos0;
     xmax = wk.pos0 + (wk.nrows - 1) * p.x_pos_stride;
     xgroup = p.xseg[wk.xseg].group;
   }
   __device__ __forceinline__ bool next(const BwdParams& p) {
-    while (gi < p.n_inner) {
-      while (seg < p.n_yseg) {
-        const KSegD s = p.yseg[seg];
-        const int nt = (s.group == xgroup) ? (s.nrows + BY - 1) / BY : 0;
-        while (++yt < nt) {
-          const int r0 = yt * BY;
-          const int nv = min(BY, s.nrows - r0);
-          const int ya = s.pos0 + r0 * p.y_pos_stride;
-          const int yb = ya + (nv - 1) * p.y_pos_stride;
-          if (p.wr >= 0 && ya - xmax > p.wr) break;
-          if (p.wl >= 0 && xmin - yb > p.wl) continue;
-          y_row0 = s.row0 + r0; nvalid = nv; ypos0 = ya; flag = s.flag;
-          return true;
-        }
-        ++seg; yt = -1;
+    for (;;) {
+      if (++yt < yt_end) {
+        const int r0 = yt * BY;
+        y_row0 = s_row0 + r0;
+        nvalid = min(BY, s_nrows - r0);
+        ypos0 = s_pos0 + r0 * p.y_pos_stride;
+        flag = s_flag;
+        return true;
       }
-      ++gi; seg = 0; yt = -1;
+      if (++seg >= p.n_yseg) {
+        seg = 0;
+        if (p.n_yseg == 0 || ++gi >= p.n_inner) return false;
+      }
+      const KSegD s = p.yseg[seg];
+      s_row0 = s.row0; s_nrows = s.nrows; s_pos0 = s.pos0; s_flag = s.flag;
+      const int nt = (s.group == xgroup) ? (s.nrows + BY - 1) / BY : 0;
+      int lo = 0, hi = nt;
+      if (p.wr >= 0 && nt > 0) {            // a tile is right of the window iff ypos0 - xmax > wr
+        const int lim = xmax + p.wr - s.pos0;
+        hi = lim < 0 ? 0 : min(nt, lim / (BY * p.y_pos_stride) + 1);
+      }
+      if (p.wl >= 0 && hi > 0) {            // ... left of it iff xmin - (position of its last valid row) > wl
+        const int need = xmin - p.wl - s.pos0;
+        if (need > 0) {
+          const int e_min = (need + p.y_pos_stride - 1) / p.y_pos_stride + 1;   // rows the tile prefix must span
+          lo = e_min > s.nrows ? hi : (e_min + BY - 1) / BY - 1;
+        }
+      }
+      yt = lo - 1;
+      yt_end = hi;
     }
-    return false;
+  }
+};
+
+// stage index + phase bit of a ring of N mbarrier-guarded buffers (no division on the single-thread roles' paths)
+template <int N>
+struct Ring {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++idx == N) { idx = 0; phase ^= 1u; }
   }
 };
 
@@ -306,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     if (warp == kTmaWarp) {
       // =========================================================== producer (whole warp: lane 0 drives TMA,
       // all lanes fetch the per-column lse2/delta of streamed query tiles in the dKV pass)
-      uint32_t xc = 0, yc = 0;
+      uint32_t xc = 0;
+      Ring<C::STAGES> yr;           // streamed-tile ring (stage index + phase), advanced once per tile
       int x_ok = -1, y_ok = -1;     // last arrival flags already acquired (a flag only ever needs one acquire per launch)
       for (int round = 0;; ++round) {
         Work wk;
@@ -325,32 +354,34 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
         ++xc;
         TileIter<BY> it;
         it.init(p, wk);
+        const int hy0 = kIsDKV ? wk.hx * p.n_inner : wk.hx / p.hx_per_hy;      // (one division per work item, not per tile)
+        const float* l2_b = p.lse2 + wk.b * p.stat_sb;
+        const float* dl_b = p.delta + wk.b * p.stat_sb;
         while (it.next(p)) {
-          const int hy = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx / p.hx_per_hy;
-          const uint32_t st = yc % C::STAGES;
-          const uint32_t par = (yc / C::STAGES) & 1;
+          const int hy = kIsDKV ? hy0 + it.gi : hy0;
+          const uint32_t st = yr.idx;
+          const uint32_t par = yr.phase;
           if (lane == 0) {
             if (it.flag >= 0 && it.flag != y_ok) { wait_arrival(p.flags, p.flag_epoch, it.flag, p.comm.watchdog_ns); y_ok = it.flag; }
             mbar_wait(y_empty + 8 * st, par ^ 1);
             mbar_arrive_expect_tx(y_full + 8 * st, 2 * C::YTILE_BYTES);
+            const uint32_t ydst = smem + C::OFF_Y + st * 2 * C::YTILE_BYTES;
 #pragma unroll
             for (int db = 0; db < C::DBLK; ++db) {
-              tma_load_4d(smem + C::OFF_Y + st * 2 * C::YTILE_BYTES + db * C::YBLK_BYTES, &p.tm_y0, y_full + 8 * st,
-                          db * 64, hy, it.y_row0, wk.b);
-              tma_load_4d(smem + C::OFF_Y + st * 2 * C::YTILE_BYTES + C::YTILE_BYTES + db * C::YBLK_BYTES, &p.tm_y1,
-                          y_full + 8 * st, db * 64, hy, it.y_row0, wk.b);
+              tma_load_4d(ydst + db * C::YBLK_BYTES, &p.tm_y0, y_full + 8 * st, db * 64, hy, it.y_row0, wk.b);
+              tma_load_4d(ydst + C::YTILE_BYTES + db * C::YBLK_BYTES, &p.tm_y1, y_full + 8 * st, db * 64, hy, it.y_row0, wk.b);
             }
           }
           if constexpr (kIsDKV) {
             // per-column statistics of the streamed query rows: asynchronous 4-byte copies global -> smem that arrive
             // on st_full when they land (cp.async.mbarrier.arrive.noinc), so STAGES tiles of statistics are in flight.
             // Round 2 finding: the synchronous ld.global -> st.shared -> arrive this replaces cost one global-load
-            // latency PER TILE on the producer's critical path and bounded the whole dK/dV pass (32-row tiles took
-            // as long per tile as 64-row tiles).  Invalid columns are zero-filled (their scores are masked anyway).
+            // latency PER TILE on the producer's critical path and bounded the whole dK/dV pass.  Invalid columns are
+            // zero-filled (their scores are masked anyway).
             __syncwarp();                      // lane 0 has acquired the arrival flag of this tile's rows
             mbar_wait(st_empty + 8 * st, par ^ 1);
-            const float* l2 = p.lse2 + wk.b * p.stat_sb + hy * p.stat_sh;
-            const float* dl = p.delta + wk.b * p.stat_sb + hy * p.stat_sh;
+            const float* l2 = l2_b + hy * p.stat_sh;
+            const float* dl = dl_b + hy * p.stat_sh;
             const uint32_t sdst = smem + C::OFF_STAT + st * 2 * BY * 4;
 #pragma unroll
             for (int i = 0; i < BY / 32; ++i) {
@@ -361,46 +392,65 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
             }
             cp_async_mbar_arrive_noinc(st_full + 8 * st);
           }
-          ++yc;
+          yr.advance();
         }
       }
     } else if (warp == kMmaWarp) {
       // =========================================================== MMA issuer (whole warp, elected lane issues)
+      // This warp's instruction stream is on the critical path of every streamed tile (round-2 ncu: the element-wise
+      // warpgroups waited on t_full 60-70 % of the time while the tensor pipe sat at 55-60 %: the issuer executed
+      // ~240 mostly dependent uniform-datapath instructions per tile).  Hence: shared-memory descriptors are built
+      // ONCE and stepped by adding (byte offset >> 4) to their low word, ring indices / phases are counters (no
+      // division), and the tile iterator is the range form above.
       {
         constexpr uint32_t idesc_t = make_idesc_f16(kBf16 ? 1 : 0, BX, BY, 0, 0);
         constexpr uint32_t idesc_acc = make_idesc_f16(kBf16 ? 1 : 0, BX, kD, 0, 1);
-        uint32_t xc = 0, yc = 0, ac = 0;
-        uint32_t g = 0;        // streamed tiles issued so far by this CTA: tile g lives in TMEM stage g % NS, phase g / NS
-        auto issue_t = [&](uint32_t stage, int s) {
-          const uint32_t x0 = smem + C::OFF_X, x1 = x0 + C::XTILE_BYTES;
-          const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
+        constexpr uint32_t kYStage16 = (2 * C::YTILE_BYTES) >> 4;        // descriptor step per smem stage
+        const uint64_t dx0 = make_sw128_desc(smem + C::OFF_X, 16, 1024);                       // X0, K-major
+        const uint64_t dx1 = make_sw128_desc(smem + C::OFF_X + C::XTILE_BYTES, 16, 1024);      // X1
+        const uint64_t dyt = make_sw128_desc(smem + C::OFF_Y, 16, 1024);                       // Y0 of stage 0 as the K-major B operand
+        const uint64_t dya = make_sw128_desc(smem + C::OFF_Y, C::YBLK_BYTES, 1024);            // ... as the MN-major B operand
+        uint32_t xc = 0, ac = 0;
+        Ring<C::STAGES> yi;        // smem stage of the next tile whose T GEMMs are issued
+        Ring<C::STAGES> ya;        // smem stage of the next tile whose accumulate GEMMs are issued
+        Ring<NS> ti;               // TMEM stage (+ t_full phase) of the next T issue
+        Ring<NS> ta;               // TMEM stage (+ p_full phase) of the next accumulate issue
+        auto issue_t = [&](uint32_t stage, uint32_t s) {
+          const uint32_t so = stage * kYStage16;
+          const uint32_t d0 = tmem + C::TMEM_T0 + s * BY, d1 = tmem + C::TMEM_T1 + s * BY;
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
             const uint32_t xo = (kk >> 2) * C::XBLK_BYTES + (kk & 3) * 32;
             const uint32_t yo = (kk >> 2) * C::YBLK_BYTES + (kk & 3) * 32;
-            mma_ss(tmem + C::TMEM_T0 + s * BY, make_sw128_desc(x0 + xo, 16, 1024), make_sw128_desc(y0 + yo, 16, 1024),
-                   idesc_t, kk > 0 ? 1u : 0u);
+            mma_ss(d0, desc_step(dx0, xo >> 4), desc_step(dyt, so + (yo >> 4)), idesc_t, kk > 0 ? 1u : 0u);
           }
 #pragma unroll
           for (int kk = 0; kk < kD / 16; ++kk) {
             const uint32_t xo = (kk >> 2) * C::XBLK_BYTES + (kk & 3) * 32;
-            const uint32_t yo = (kk >> 2) * C::YBLK_BYTES + (kk & 3) * 32;
-            mma_ss(tmem + C::TMEM_T1 + s * BY, make_sw128_desc(x1 + xo, 16, 1024), make_sw128_desc(y1 + yo, 16, 1024),
-                   idesc_t, kk > 0 ? 1u : 0u);
+            const uint32_t yo = C::YTILE_BYTES + (kk >> 2) * C::YBLK_BYTES + (kk & 3) * 32;
+            mma_ss(d1, desc_step(dx1, xo >> 4), desc_step(dyt, so + (yo >> 4)), idesc_t, kk > 0 ? 1u : 0u);
           }
         };
-        auto issue_acc = [&](uint32_t stage, int s, bool acc) {
-          const uint32_t y0 = smem + C::OFF_Y + stage * 2 * C::YTILE_BYTES, y1 = y0 + C::YTILE_BYTES;
+        auto issue_acc = [&](uint32_t stage, uint32_t s, bool acc) {
+          const uint32_t so = stage * kYStage16;
+          const uint32_t a1 = tmem + C::TMEM_T1 + s * BY, a0 = tmem + C::TMEM_T0 + s * BY;
 #pragma unroll
           for (int kk = 0; kk < BY / 16; ++kk)   // acc0 += dS * Y0
-            mma_ts(tmem + C::TMEM_ACC0, tmem + C::TMEM_T1 + s * BY + kk * 8,
-                   make_sw128_desc(y0 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+            mma_ts(tmem + C::TMEM_ACC0, a1 + kk * 8, desc_step(dya, so + ((kk * 2048) >> 4)), idesc_acc, (acc || kk > 0) ? 1u : 0u);
           if constexpr (kIsDKV) {
 #pragma unroll
             for (int kk = 0; kk < BY / 16; ++kk)   // acc1 += P * Y1
-              mma_ts(tmem + C::TMEM_ACC1, tmem + C::TMEM_T0 + s * BY + kk * 8,
-                     make_sw128_desc(y1 + kk * 2048, C::YBLK_BYTES, 1024), idesc_acc, (acc || kk > 0) ? 1u : 0u);
+              mma_ts(tmem + C::TMEM_ACC1, a0 + kk * 8, desc_step(dya, so + ((C::YTILE_BYTES + kk * 2048) >> 4)), idesc_acc,
+                     (acc || kk > 0) ? 1u : 0u);
           }
+        };
+        auto t_step = [&]() {      // T GEMMs of the next streamed tile into the next TMEM stage
+          mbar_wait(y_full + 8 * yi.idx, yi.phase);
+          tc_fence_after();
+          issue_t(yi.idx, ti.idx);
+          mma_commit(t_full + 8 * ti.idx);
+          yi.advance();
+          ti.advance();
         };
         for (int round = 0;; ++round) {
           Work wk;
@@ -409,48 +459,35 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
           it.init(p, wk);
           mbar_wait(x_full, xc & 1);
           ++xc;
-          bool have = it.next(p);
-          if (!have) {
+          bool more = it.next(p);
+          if (!more) {
             mma_commit(x_empty);
             continue;
           }
           tc_fence_after();
           // prologue: the T GEMMs of the first NS tiles (as far as present)
-          // (the smem stage of streamed tile g is g % STAGES: yc == g when its T GEMMs are issued)
-          int n_issued = 0;
-          bool more = have;
-          const uint32_t g0 = g;
+          int pending = 0;                         // tiles whose T GEMMs are issued and whose accumulate GEMMs are not
           for (int i = 0; i < NS && more; ++i) {
-            const uint32_t st = yc % C::STAGES;
-            const int s = static_cast<int>((g0 + i) % NS);
-            mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
-            ++yc;
-            tc_fence_after();
-            issue_t(st, s);
-            mma_commit(t_full + 8 * s);
-            ++n_issued;
+            t_step();
+            ++pending;
             more = it.next(p);
           }
           if (!more) mma_commit(x_empty);          // all T GEMMs (the only readers of X) are issued
-          for (int j = 0; j < n_issued; ++j, ++g) {
-            const int s = static_cast<int>(g % NS);
-            mbar_wait(p_full + 8 * s, (g / NS) & 1);
-            if (j == 0) {
+          for (bool first = true; pending > 0; first = false) {
+            mbar_wait(p_full + 8 * ta.idx, ta.phase);
+            if (first) {
               mbar_wait(acc_empty, (ac & 1) ^ 1);
               ++ac;
             }
             tc_fence_after();
-            const uint32_t sq = g % C::STAGES;
-            issue_acc(sq, s, j > 0);
-            mma_commit(y_empty + 8 * sq);
-            if (more) {                              // tile j + NS takes over the TMEM stage that was just consumed
-              const uint32_t st = yc % C::STAGES;
-              mbar_wait(y_full + 8 * st, (yc / C::STAGES) & 1);
-              ++yc;
-              tc_fence_after();
-              issue_t(st, s);
-              mma_commit(t_full + 8 * s);
-                ++n_issued;
+            issue_acc(ya.idx, ta.idx, !first);
+            mma_commit(y_empty + 8 * ya.idx);
+            ya.advance();
+            ta.advance();
+            --pending;
+            if (more) {                              // the next tile takes over the TMEM stage that was just consumed
+              t_step();
+              ++pending;
               more = it.next(p);
               if (!more) mma_commit(x_empty);
             }
@@ -466,7 +503,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
     const int wg = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    uint32_t g = 0, yc = 0, afc = 0, xcw = 0;
+    uint32_t g = 0, afc = 0, xcw = 0;
+    Ring<C::STAGES> yr;      // smem stage (+ phase) of the current streamed tile
+    Ring<NS> tr;             // TMEM stage (+ phase) of the current streamed tile
     const bool plain = (p.softcap == 0.f) && (p.alibi == nullptr);
     for (int round = 0;; ++round) {
       Work wk;
@@ -492,17 +531,19 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_bwd_kernel(const __grid_cons
       it.init(p, wk);
       int j = 0;
       while (it.next(p)) {
-        const uint32_t st = yc % C::STAGES;
-        const uint32_t ypar = (yc / C::STAGES) & 1;
-        ++yc;
+        const uint32_t st = yr.idx;
+        const uint32_t ypar = yr.phase;
+        const int sT = static_cast<int>(tr.idx);                  // TMEM stage of this tile
+        const uint32_t tpar = tr.phase;
+        yr.advance();
+        tr.advance();
         const uint32_t gt = g++;
         if (static_cast<int>(gt & 1u) != wg) { ++j; continue; }   // warpgroup wg owns the tiles with g % 2 == wg
-        const int sT = static_cast<int>(gt % NS);                 // TMEM stage of this tile
         const uint32_t tT0 = tmem + lane_base + C::TMEM_T0 + sT * BY, tT1 = tmem + lane_base + C::TMEM_T1 + sT * BY;
         constexpr int h_begin = 0, h_end = BY / 32;               // 32-column halves per tile
         const int hq = kIsDKV ? wk.hx * p.n_inner + it.gi : wk.hx;     // query head (ALiBi slope index)
         const float slope = p.alibi ? p.alibi[wk.b * p.alibi_bstride + hq] : 0.f;
-        mbar_wait(t_full + 8 * sT, (gt / NS) & 1);
+        mbar_wait(t_full + 8 * sT, tpar);
         if constexpr (kIsDKV) mbar_wait(st_full + 8 * st, ypar);
         tc_fence_after();
         const int yb = it.ypos0 + (it.nvalid - 1) * p.y_pos_stride;

@@ -86,39 +86,62 @@ __device__ __forceinline__ int sched_work(int round, int n_comm) {
 }
 
 // Deterministic enumeration of the K/V tiles a Q pair has to visit (identical in every role).
+// Positions grow with the tile index inside a segment, so the visible tiles of a segment are ONE contiguous range
+// [lo, hi) computed when the iterator enters the segment; the per-tile step is a compare and three multiply-adds
+// (the single-thread roles -- MMA issuer, TMA producer -- are the critical path of this kernel, see the round-2
+// profile in profiles/r2/; tests/test_properties_cpu.py checks the range form against the per-tile window tests).
 struct TileIter {
-  int seg, kt;
+  int seg, kt, kt_end;
   int qmin, qmax, qgroup;
+  int s_row0, s_nrows, s_pos0, s_flag;    // current segment (cached)
   // current tile
   int k_row0, nvalid, kpos0, flag;
   __device__ __forceinline__ void init(const FwdParams& p, const Work& wk) {
-    seg = 0;
-    kt = -1;
+    seg = -1;
+    kt = 0;
+    kt_end = 0;
     qmin = wk.pos0;
     qmax = wk.pos0 + (wk.nrows - 1) * p.q_pos_stride;
     qgroup = p.qseg[wk.qseg].group;
   }
   __device__ __forceinline__ bool next(const FwdParams& p) {
-    while (seg < p.n_kseg) {
-      const KSegD s = p.kseg[seg];
-      const int nt = (s.group == qgroup) ? (s.nrows + BN - 1) / BN : 0;
-      while (++kt < nt) {
+    for (;;) {
+      if (++kt < kt_end) {
         const int r0 = kt * BN;
-        const int nv = min(BN, s.nrows - r0);
-        const int ka = s.pos0 + r0 * p.k_pos_stride;
-        const int kb = ka + (nv - 1) * p.k_pos_stride;
-        if (p.wr >= 0 && ka - qmax > p.wr) break;   // later tiles are further right
-        if (p.wl >= 0 && qmin - kb > p.wl) continue;               // entirely left of the window
-        k_row0 = s.row0 + r0;
-        nvalid = nv;
-        kpos0 = ka;
-        flag = s.flag;
+        k_row0 = s_row0 + r0;
+        nvalid = min(BN, s_nrows - r0);
+        kpos0 = s_pos0 + r0 * p.k_pos_stride;
+        flag = s_flag;
         return true;
       }
-      ++seg;
-      kt = -1;
+      if (++seg >= p.n_kseg) return false;
+      const KSegD s = p.kseg[seg];
+      s_row0 = s.row0; s_nrows = s.nrows; s_pos0 = s.pos0; s_flag = s.flag;
+      const int nt = (s.group == qgroup) ? (s.nrows + BN - 1) / BN : 0;
+      int lo = 0, hi = nt;
+      if (p.wr >= 0 && nt > 0) {            // a tile is right of the window iff kpos0 - qmax > wr
+        const int lim = qmax + p.wr - s.pos0;
+        hi = lim < 0 ? 0 : min(nt, lim / (BN * p.k_pos_stride) + 1);
+      }
+      if (p.wl >= 0 && hi > 0) {            // ... left of it iff qmin - (position of its last valid row) > wl
+        const int need = qmin - p.wl - s.pos0;
+        if (need > 0) {
+          const int e_min = (need + p.k_pos_stride - 1) / p.k_pos_stride + 1;   // rows the tile prefix must span
+          lo = e_min > s.nrows ? hi : (e_min + BN - 1) / BN - 1;
+        }
+      }
+      kt = lo - 1;
+      kt_end = hi;
     }
-    return false;
+  }
+};
+
+// stage index + phase bit of a ring of N mbarrier-guarded buffers (no division on the single-thread roles' paths)
+template <int N>
+struct Ring {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance() {
+    if (++idx == N) { idx = 0; phase ^= 1u; }
   }
 };
 
@@ -254,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
     // =========================================================== TMA producer
     if (lane == 0) {
       uint32_t qc[2] = {0, 0};
-      uint32_t kvc = 0;
+      Ring<C::STAGES> kr;
       int q_flag_ok = -1, k_flag_ok = -1;
       for (int round = 0;; ++round) {
         Work wk;
@@ -277,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           if (it.flag >= 0 && it.flag != k_flag_ok) { wait_flag(p, it.flag); k_flag_ok = it.flag; }
 #pragma unroll
           for (int kv = 0; kv < 2; ++kv) {
-            const uint32_t slot = kvc % C::STAGES;
-            const uint32_t par = (kvc / C::STAGES) & 1;
+            const uint32_t slot = kr.idx;
+            const uint32_t par = kr.phase;
             mbar_wait(B.kv_empty + 8 * slot, par ^ 1);
             mbar_arrive_expect_tx(B.kv_full + 8 * slot, C::TILE_BYTES);
 #pragma unroll
@@ -286,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
               tma_load_4d(smem + C::OFF_KV + slot * C::TILE_BYTES + db * C::BLK_BYTES,
                           kv == 0 ? &p.tm_k : &p.tm_v, B.kv_full + 8 * slot, db * 64, hk,
                           it.k_row0, wk.b);
-            ++kvc;
+            kr.advance();
           }
         }
       }
@@ -294,27 +317,32 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
    } else if (warp == kMmaWarp) {
     // =========================================================== MMA issuer (whole warp, elected lane issues)
     {
+      // This warp's instruction stream is on the critical path of every K/V tile (round-2 ncu: the softmax warpgroups
+      // waited on s_full 44 % of the time with the tensor pipe at 50 %): descriptors are built once and stepped with
+      // one add on their low word, ring slots / phases are counters, the tile iterator is the range form.
       constexpr uint32_t idesc_qk = make_idesc_f16(kBf16 ? 1 : 0, BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(kBf16 ? 1 : 0, BM, kD, 0, 1);
+      constexpr uint32_t kStage16 = C::TILE_BYTES >> 4;
+      const uint64_t dq0 = make_sw128_desc(smem + C::OFF_Q, 16, 1024);                   // Q tile 0 (tile 1: + TILE_BYTES)
+      const uint64_t dkk = make_sw128_desc(smem + C::OFF_KV, 16, 1024);                  // K/V slot 0 as the K-major B operand
+      const uint64_t dvv = make_sw128_desc(smem + C::OFF_KV, C::BLK_BYTES, 1024);        // ... as the MN-major B operand
       uint32_t qc[2] = {0, 0}, pc[2] = {0, 0};
-      uint32_t kvc = 0;
+      Ring<C::STAGES> kr;
       auto issue_qk = [&](int t, uint32_t kslot) {
-        const uint32_t qa = smem + C::OFF_Q + t * C::TILE_BYTES;
-        const uint32_t ka = smem + C::OFF_KV + kslot * C::TILE_BYTES;
+        const uint32_t ko = kslot * kStage16;
+        const uint32_t qo = t * kStage16;
 #pragma unroll
         for (int kk = 0; kk < kD / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * C::BLK_BYTES + (kk & 3) * 32;
-          mma_ss(tmem + C::TMEM_S + t * 128, make_sw128_desc(qa + off, 16, 1024),
-                 make_sw128_desc(ka + off, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+          const uint32_t off = ((kk >> 2) * C::BLK_BYTES + (kk & 3) * 32) >> 4;
+          mma_ss(tmem + C::TMEM_S + t * 128, desc_step(dq0, qo + off), desc_step(dkk, ko + off), idesc_qk, kk > 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int t, uint32_t vslot, bool acc) {
-        const uint32_t va = smem + C::OFF_KV + vslot * C::TILE_BYTES;
+        const uint32_t vo = vslot * kStage16;
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk) {
-          mma_ts(tmem + C::TMEM_O + t * kD, tmem + C::TMEM_S + t * 128 + kk * 8,
-                 make_sw128_desc(va + kk * 2048, C::BLK_BYTES, 1024), idesc_pv,
-                 (acc || kk > 0) ? 1u : 0u);
+          mma_ts(tmem + C::TMEM_O + t * kD, tmem + C::TMEM_S + t * 128 + kk * 8, desc_step(dvv, vo + ((kk * 2048) >> 4)),
+                 idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
       for (int round = 0;; ++round) {
@@ -333,9 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
           continue;
         }
         // first tile: S_t = Q_t K_0^T
-        uint32_t kslot = kvc % C::STAGES;
-        mbar_wait(B.kv_full + 8 * kslot, (kvc / C::STAGES) & 1);
-        ++kvc;
+        uint32_t kslot = kr.idx;
+        mbar_wait(B.kv_full + 8 * kslot, kr.phase);
+        kr.advance();
         tc_fence_after();
         for (int t = 0; t < nt; ++t) {
           issue_qk(t, kslot);
@@ -343,15 +371,15 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         }
         mma_commit(B.kv_empty + 8 * kslot);
         for (int j = 0;; ++j) {
-          const uint32_t vslot = kvc % C::STAGES;
-          const uint32_t vpar = (kvc / C::STAGES) & 1;
-          ++kvc;
+          const uint32_t vslot = kr.idx;
+          const uint32_t vpar = kr.phase;
+          kr.advance();
           const bool have_next = it.next(p);
           uint32_t kpar = 0;
           if (have_next) {
-            kslot = kvc % C::STAGES;
-            kpar = (kvc / C::STAGES) & 1;
-            ++kvc;
+            kslot = kr.idx;
+            kpar = kr.phase;
+            kr.advance();
           }
           mbar_wait(B.kv_full + 8 * vslot, vpar);
           for (int t = 0; t < nt; ++t) {
@@ -444,12 +472,23 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
             tmem_wait_ld();
             tmem_ld32(tS + 64, *reinterpret_cast<uint32_t(*)[32]>(&v[64]));
             tmem_ld32(tS + 96, *reinterpret_cast<uint32_t(*)[32]>(&v[96]));
+            // four independent chains: one serial FMNMX3 chain over 128 values was ~300 clk of pure dependency latency
+            // on the critical path of every tile (two warps per scheduler cannot hide it)
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+            for (int c = 0; c < 64; c += 8) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                m4[i] = fmaxf(m4[i], fmaxf(__uint_as_float(v[c + 2 * i]), __uint_as_float(v[c + 2 * i + 1])));
+            }
             tmem_wait_ld();
 #pragma unroll
-            for (int c = 64; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-            mx *= p.scale_log2;
+            for (int c = 64; c < 128; c += 8) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                m4[i] = fmaxf(m4[i], fmaxf(__uint_as_float(v[c + 2 * i]), __uint_as_float(v[c + 2 * i + 1])));
+            }
+            mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2;
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));

@@ -261,6 +261,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same descriptor, start address advanced by `step16` units of 16 bytes: ONE 32-bit add on the low word (the address
+// field is bits [0,14) and shared-memory addresses stay below 2^18, so the sum cannot carry into the LBO field).
+__device__ __forceinline__ uint64_t desc_step(uint64_t base, uint32_t step16) {
+  return (base & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(static_cast<uint32_t>(base) + step16);
+}
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp32 accumulate.
 // fmt: 0 = f16, 1 = bf16.  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int fmt, int M, int N, int a_mn, int b_mn) {

@@ -112,9 +112,8 @@ def test_chunk_by_group_keeps_groups_whole_and_within_the_segment_budget(segs_pe
     assert sorted(seen_q) == sorted(qrows) and sorted(seen_k) == sorted(krows)
 
 
-def _tile_iter_twin(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN):
-    """Python transcription of the kernels' ``TileIter::next`` (``csrc/fmha_fwd_sm100.cu``; the backward's iterator is
-    the same with X/Y renamed): K/V tiles a block of query rows visits, tiles fully outside the window skipped."""
+def _tile_iter_per_tile(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN):
+    """The window tests tile by tile (the kernels' round-1 iterator): the definition the range form must reproduce."""
     qmin, qmax = q_pos0, q_pos0 + (q_rows - 1) * q_stride
     visited = []
     for si, (row0, nrows, pos0, group) in enumerate(ksegs):
@@ -130,6 +129,41 @@ def _tile_iter_twin(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, 
                 continue                                # entirely left of the window
             visited.append((si, kt))
     return visited
+
+
+def _tile_iter_twin(q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN):
+    """Python transcription of the kernels' ``TileIter::next`` (``csrc/fmha_fwd_sm100.cu``; the backward's iterator is
+    the same with X/Y renamed): K/V tiles a block of query rows visits.  Positions grow with the tile index inside a
+    segment, so the visible tiles are one contiguous range ``[lo, hi)`` per segment, computed on segment entry (C++
+    integer division: every dividend below is non-negative)."""
+    qmin, qmax = q_pos0, q_pos0 + (q_rows - 1) * q_stride
+    visited = []
+    for si, (row0, nrows, pos0, group) in enumerate(ksegs):
+        nt = (nrows + BN - 1) // BN if group == q_group else 0
+        lo, hi = 0, nt
+        if wr >= 0 and nt > 0:
+            lim = qmax + wr - pos0
+            hi = 0 if lim < 0 else min(nt, lim // (BN * k_stride) + 1)
+        if wl >= 0 and hi > 0:
+            need = qmin - wl - pos0
+            if need > 0:
+                e_min = (need + k_stride - 1) // k_stride + 1
+                lo = hi if e_min > nrows else (e_min + BN - 1) // BN - 1
+        visited += [(si, kt) for kt in range(lo, hi)]
+    return visited
+
+
+@settings(max_examples=500, deadline=None)
+@given(st.integers(0, 300), st.integers(1, 24), st.sampled_from([1, 2, 4]), st.integers(0, 1),
+       st.lists(st.tuples(st.integers(1, 40), st.integers(0, 300), st.integers(0, 1)), min_size=1, max_size=4),
+       st.sampled_from([1, 2, 4]), st.integers(-1, 64), st.integers(-1, 64), st.sampled_from([4, 8]))
+def test_tile_range_form_equals_the_per_tile_window_tests(q_pos0, q_rows, q_stride, q_group, kdefs, k_stride, wl, wr, BN):
+    ksegs, row = [], 0
+    for nrows, pos0, group in kdefs:
+        ksegs.append((row, nrows, pos0, group))
+        row += nrows
+    a = (q_pos0, q_rows, q_stride, q_group, ksegs, k_stride, wl, wr, BN)
+    assert _tile_iter_twin(*a) == _tile_iter_per_tile(*a)
 
 
 @settings(max_examples=300, deadline=None)
