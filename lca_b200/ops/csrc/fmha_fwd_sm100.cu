@@ -352,12 +352,20 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         TileIter it;
         it.init(p, wk);
         bool have = it.next(p);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(B.q_full[t], qc[t] & 1);
-          ++qc[t];
+        // every loop over the two Q tiles is unrolled with a compile-time tile index: barrier addresses, TMEM columns and
+        // descriptor offsets stay in uniform registers (a runtime index cost an R2UR + ELECT per tcgen05.mma: 106 R2UR
+        // per K/V tile pair in the round-2 profile)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nt) {
+            mbar_wait(B.q_full[t], qc[t] & 1);
+            ++qc[t];
+          }
         }
         if (!have) {
-          for (int t = 0; t < nt; ++t) mma_commit(B.o_full[t]);      // empty item: hand the Q tiles back
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            if (t < nt) mma_commit(B.o_full[t]);      // empty item: hand the Q tiles back
           continue;
         }
         // first tile: S_t = Q_t K_0^T
@@ -365,9 +373,12 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
         mbar_wait(B.kv_full + 8 * kslot, kr.phase);
         kr.advance();
         tc_fence_after();
-        for (int t = 0; t < nt; ++t) {
-          issue_qk(t, kslot);
-          mma_commit(B.s_full[t]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nt) {
+            issue_qk(t, kslot);
+            mma_commit(B.s_full[t]);
+          }
         }
         mma_commit(B.kv_empty + 8 * kslot);
         for (int j = 0;; ++j) {
@@ -382,22 +393,25 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_kernel(const __grid_cons
             kr.advance();
           }
           mbar_wait(B.kv_full + 8 * vslot, vpar);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(B.p_full[t], pc[t] & 1);
-            ++pc[t];
-            tc_fence_after();
-            issue_pv(t, vslot, j > 0);
-            if (t == nt - 1) mma_commit(B.kv_empty + 8 * vslot);
-            if (have_next) {
-              if (t == 0) {
-                mbar_wait(B.kv_full + 8 * kslot, kpar);
-                tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t < nt) {
+              mbar_wait(B.p_full[t], pc[t] & 1);
+              ++pc[t];
+              tc_fence_after();
+              issue_pv(t, vslot, j > 0);
+              if (t == nt - 1) mma_commit(B.kv_empty + 8 * vslot);
+              if (have_next) {
+                if (t == 0) {
+                  mbar_wait(B.kv_full + 8 * kslot, kpar);
+                  tc_fence_after();
+                }
+                issue_qk(t, kslot);
+                mma_commit(B.s_full[t]);
+                if (t == nt - 1) mma_commit(B.kv_empty + 8 * kslot);
+              } else {
+                mma_commit(B.o_full[t]);
               }
-              issue_qk(t, kslot);
-              mma_commit(B.s_full[t]);
-              if (t == nt - 1) mma_commit(B.kv_empty + 8 * kslot);
-            } else {
-              mma_commit(B.o_full[t]);
             }
           }
           if (!have_next) break;
