@@ -1,5 +1,5 @@
-// FP8 (e4m3) forward flash attention for sm_100a -- EXPERIMENTAL (compile-checked; hardware validation is the
-// first item of the next GPU session; gated behind LCA_B200_EXPERIMENTAL_FP8=1).
+// FP8 (e4m3) forward flash attention for sm_100a (validated on B200 in round 2 against the PyTorch emulation of its
+// arithmetic, tests/test_fp8.py; reached through AttnType.SAGE_FP8* / SAGE_AUTO, ops/fp8.py).
 //
 // Same warp-specialised structure as fmha_fwd_sm100.cu (this file is derived from it), with 1-byte operands:
 //   * Q/K/V tiles are [128 rows][128 B] (head_dim 128 only), TMA box (128, 1, 128, 1) over a uint8 tensor map;
@@ -43,79 +43,7 @@ struct Cfg {
   static constexpr int TMEM_O = 256;                   // O_t at column 256 + t*kD
 };
 
-struct Work {
-  int qseg, seg_row0, row0, nrows, pos0, b, h, ntile;
-};
-
-__device__ __forceinline__ bool decode_work(const FwdParams& p, int w, Work& wk) {
-  if (w >= p.total_work) return false;
-  const int bh = p.B * p.H;
-  int pr = w / bh;
-  const int r = w - pr * bh;
-  wk.b = r / p.H;
-  wk.h = r - wk.b * p.H;
-  for (int s = 0; s < p.n_qseg; ++s) {
-    const int np = (p.qseg[s].nrows + 2 * BM - 1) / (2 * BM);
-    if (pr < np) {
-      const int pi = np - 1 - pr;  // heaviest (latest positions) first
-      wk.qseg = s;
-      wk.seg_row0 = pi * 2 * BM;
-      wk.row0 = p.qseg[s].row0 + wk.seg_row0;
-      wk.nrows = min(2 * BM, p.qseg[s].nrows - wk.seg_row0);
-      wk.pos0 = p.qseg[s].pos0 + wk.seg_row0 * p.q_pos_stride;
-      wk.ntile = wk.nrows > BM ? 2 : 1;
-      return true;
-    }
-    pr -= np;
-  }
-  return false;
-}
-
-// static "snake" schedule: round k visits work k*G + c on even rounds and k*G + (G-1-c) on odd
-// rounds, which cancels the cost gradient of the heaviest-first ordering across CTAs.
-__device__ __forceinline__ int sched_work(int round, int n_comm) {
-  const int G = static_cast<int>(gridDim.x) - n_comm;          // compute CTAs
-  const int me = static_cast<int>(blockIdx.x) - n_comm;
-  const int c = (round & 1) ? (G - 1 - me) : me;
-  return round * G + c;
-}
-
-// Deterministic enumeration of the K/V tiles a Q pair has to visit (identical in every role).
-struct TileIter {
-  int seg, kt;
-  int qmin, qmax, qgroup;
-  // current tile
-  int k_row0, nvalid, kpos0, flag;
-  __device__ __forceinline__ void init(const FwdParams& p, const Work& wk) {
-    seg = 0;
-    kt = -1;
-    qmin = wk.pos0;
-    qmax = wk.pos0 + (wk.nrows - 1) * p.q_pos_stride;
-    qgroup = p.qseg[wk.qseg].group;
-  }
-  __device__ __forceinline__ bool next(const FwdParams& p) {
-    while (seg < p.n_kseg) {
-      const KSegD s = p.kseg[seg];
-      const int nt = (s.group == qgroup) ? (s.nrows + BN - 1) / BN : 0;
-      while (++kt < nt) {
-        const int r0 = kt * BN;
-        const int nv = min(BN, s.nrows - r0);
-        const int ka = s.pos0 + r0 * p.k_pos_stride;
-        const int kb = ka + (nv - 1) * p.k_pos_stride;
-        if (p.wr >= 0 && ka - qmax > p.wr) break;   // later tiles are further right
-        if (p.wl >= 0 && qmin - kb > p.wl) continue;               // entirely left of the window
-        k_row0 = s.row0 + r0;
-        nvalid = nv;
-        kpos0 = ka;
-        flag = s.flag;
-        return true;
-      }
-      ++seg;
-      kt = -1;
-    }
-    return false;
-  }
-};
+#include "fmha_fwd_common.cuh"   // Work, decode_work, sched_work, TileIter, Ring
 
 __device__ __forceinline__ void wait_flag(const FwdParams& p, int idx) {
   wait_arrival(p.flags, p.flag_epoch, idx, p.comm.watchdog_ns);
@@ -232,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
     // =========================================================== TMA producer
     if (lane == 0) {
       uint32_t qc[2] = {0, 0};
-      uint32_t kvc = 0;
+      Ring<C::STAGES> kr;
       int q_flag_ok = -1, k_flag_ok = -1;
       for (int round = 0;; ++round) {
         Work wk;
@@ -255,8 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
           if (it.flag >= 0 && it.flag != k_flag_ok) { wait_flag(p, it.flag); k_flag_ok = it.flag; }
 #pragma unroll
           for (int kv = 0; kv < 2; ++kv) {
-            const uint32_t slot = kvc % C::STAGES;
-            const uint32_t par = (kvc / C::STAGES) & 1;
+            const uint32_t slot = kr.idx;
+            const uint32_t par = kr.phase;
             mbar_wait(B.kv_empty + 8 * slot, par ^ 1);
             mbar_arrive_expect_tx(B.kv_full + 8 * slot, C::TILE_BYTES);
 #pragma unroll
@@ -264,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
               tma_load_4d(smem + C::OFF_KV + slot * C::TILE_BYTES + db * C::BLK_BYTES,
                           kv == 0 ? &p.tm_k : &p.tm_v, B.kv_full + 8 * slot, db * 128, hk,
                           it.k_row0, wk.b);
-            ++kvc;
+            kr.advance();
           }
         }
       }
@@ -272,27 +200,30 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
    } else if (warp == kMmaWarp) {
     // =========================================================== MMA issuer (whole warp, elected lane issues)
     {
+      // (same issue-path diet as fmha_fwd_sm100.cu: descriptors built once and stepped by one add, ring counters,
+      //  compile-time tile index so every tcgen05.mma operand stays in uniform registers)
       constexpr uint32_t idesc_qk = make_idesc_f8(BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f8(BM, kD, 0, 1);
+      constexpr uint32_t kStage16 = C::TILE_BYTES >> 4;
+      const uint64_t dq0 = make_sw128_desc(smem + C::OFF_Q, 16, 1024);
+      const uint64_t dkk = make_sw128_desc(smem + C::OFF_KV, 16, 1024);
+      const uint64_t dvv = make_sw128_desc(smem + C::OFF_KV, C::BLK_BYTES, 1024);
       uint32_t qc[2] = {0, 0}, pc[2] = {0, 0};
-      uint32_t kvc = 0;
+      Ring<C::STAGES> kr;
       auto issue_qk = [&](int t, uint32_t kslot) {
-        const uint32_t qa = smem + C::OFF_Q + t * C::TILE_BYTES;
-        const uint32_t ka = smem + C::OFF_KV + kslot * C::TILE_BYTES;
+        const uint32_t ko = kslot * kStage16, qo = t * kStage16;
 #pragma unroll
         for (int kk = 0; kk < kD / 32; ++kk) {             // K = 32 one-byte elements per MMA
-          const uint32_t off = (kk >> 2) * C::BLK_BYTES + (kk & 3) * 32;
-          mma_ss_f8(tmem + C::TMEM_S + t * 128, make_sw128_desc(qa + off, 16, 1024),
-                    make_sw128_desc(ka + off, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+          const uint32_t off = ((kk >> 2) * C::BLK_BYTES + (kk & 3) * 32) >> 4;
+          mma_ss_f8(tmem + C::TMEM_S + t * 128, desc_step(dq0, qo + off), desc_step(dkk, ko + off), idesc_qk, kk > 0 ? 1u : 0u);
         }
       };
       auto issue_pv = [&](int t, uint32_t vslot, bool acc) {
-        const uint32_t va = smem + C::OFF_KV + vslot * C::TILE_BYTES;
+        const uint32_t vo = vslot * kStage16;
 #pragma unroll
         for (int kk = 0; kk < BN / 32; ++kk) {             // 32 key rows (= 8 TMEM columns of e4m3 P) per MMA
-          mma_ts_f8(tmem + C::TMEM_O + t * kD, tmem + C::TMEM_S + t * 128 + kk * 8,
-                    make_sw128_desc(va + kk * 4096, C::BLK_BYTES, 1024), idesc_pv,
-                    (acc || kk > 0) ? 1u : 0u);
+          mma_ts_f8(tmem + C::TMEM_O + t * kD, tmem + C::TMEM_S + t * 128 + kk * 8, desc_step(dvv, vo + ((kk * 4096) >> 4)),
+                    idesc_pv, (acc || kk > 0) ? 1u : 0u);
         }
       };
       for (int round = 0;; ++round) {
@@ -302,49 +233,58 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
         TileIter it;
         it.init(p, wk);
         bool have = it.next(p);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(B.q_full[t], qc[t] & 1);
-          ++qc[t];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nt) {
+            mbar_wait(B.q_full[t], qc[t] & 1);
+            ++qc[t];
+          }
         }
         if (!have) continue;
         // first tile: S_t = Q_t K_0^T
-        uint32_t kslot = kvc % C::STAGES;
-        mbar_wait(B.kv_full + 8 * kslot, (kvc / C::STAGES) & 1);
-        ++kvc;
+        uint32_t kslot = kr.idx;
+        mbar_wait(B.kv_full + 8 * kslot, kr.phase);
+        kr.advance();
         tc_fence_after();
-        for (int t = 0; t < nt; ++t) {
-          issue_qk(t, kslot);
-          mma_commit(B.s_full[t]);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nt) {
+            issue_qk(t, kslot);
+            mma_commit(B.s_full[t]);
+          }
         }
         mma_commit(B.kv_empty + 8 * kslot);
         for (int j = 0;; ++j) {
-          const uint32_t vslot = kvc % C::STAGES;
-          const uint32_t vpar = (kvc / C::STAGES) & 1;
-          ++kvc;
+          const uint32_t vslot = kr.idx;
+          const uint32_t vpar = kr.phase;
+          kr.advance();
           const bool have_next = it.next(p);
           uint32_t kpar = 0;
           if (have_next) {
-            kslot = kvc % C::STAGES;
-            kpar = (kvc / C::STAGES) & 1;
-            ++kvc;
+            kslot = kr.idx;
+            kpar = kr.phase;
+            kr.advance();
           }
           mbar_wait(B.kv_full + 8 * vslot, vpar);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(B.p_full[t], pc[t] & 1);
-            ++pc[t];
-            tc_fence_after();
-            issue_pv(t, vslot, j > 0);
-            if (t == nt - 1) mma_commit(B.kv_empty + 8 * vslot);
-            if (have_next) {
-              if (t == 0) {
-                mbar_wait(B.kv_full + 8 * kslot, kpar);
-                tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (t < nt) {
+              mbar_wait(B.p_full[t], pc[t] & 1);
+              ++pc[t];
+              tc_fence_after();
+              issue_pv(t, vslot, j > 0);
+              if (t == nt - 1) mma_commit(B.kv_empty + 8 * vslot);
+              if (have_next) {
+                if (t == 0) {
+                  mbar_wait(B.kv_full + 8 * kslot, kpar);
+                  tc_fence_after();
+                }
+                issue_qk(t, kslot);
+                mma_commit(B.s_full[t]);
+                if (t == nt - 1) mma_commit(B.kv_empty + 8 * kslot);
+              } else {
+                mma_commit(B.o_full[t]);
               }
-              issue_qk(t, kslot);
-              mma_commit(B.s_full[t]);
-              if (t == nt - 1) mma_commit(B.kv_empty + 8 * kslot);
-            } else {
-              mma_commit(B.o_full[t]);
             }
           }
           if (!have_next) break;
@@ -420,9 +360,14 @@ __global__ void __launch_bounds__(kThreads, 1) fmha_fwd_fp8_kernel(const __grid_
         for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
         tmem_wait_ld();
         if (!general) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};     // four independent chains
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
-          mx *= mul;
+          for (int c = 0; c < 128; c += 8) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              m4[i] = fmaxf(m4[i], fmaxf(__uint_as_float(v[c + 2 * i]), __uint_as_float(v[c + 2 * i + 1])));
+          }
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * mul;
         }
         // ---- running max with lazy rescale
         const float m_new = fmaxf(m, mx);
