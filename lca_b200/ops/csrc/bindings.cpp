@@ -314,7 +314,7 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
                       const std::vector<int64_t>& stat_offs, bool q_to_all, int64_t stage_q_rows, int64_t stage_kv_rows, const std::vector<int64_t>& peer_slabs,
                       const std::vector<int64_t>& peer_sigs, int64_t my_sig, int64_t epoch, int64_t o_target, int64_t H,
                       int64_t Hkv) {
-  TORCH_CHECK(mesh.size() == 7, "mesh arity");
+  TORCH_CHECK(mesh.size() >= 7 && mesh.size() <= 9, "mesh arity");   // [P, U, R, u, r, rows, n_comm(, kv_dst_mask, q_dst_mask)]
   const int P = static_cast<int>(mesh[0]), U = static_cast<int>(mesh[1]), R = static_cast<int>(mesh[2]);
   TORCH_CHECK(P == U * R && P <= kMaxPeers && static_cast<int>(peer_slabs.size()) == P &&
               static_cast<int>(peer_sigs.size()) == P, "peer tables");
@@ -323,6 +323,8 @@ static void fill_comm(CommParams& c, const std::vector<int64_t>& mesh, const std
   c.P = P; c.U = U; c.R = R;
   c.u = static_cast<int>(mesh[3]); c.r = static_cast<int>(mesh[4]);
   c.rows = static_cast<int>(mesh[5]);
+  c.kv_dst_mask = mesh.size() > 7 ? static_cast<unsigned int>(mesh[7]) : 0xFFFFFFFFu;   // destinations that need my K/V data
+  c.q_dst_mask = mesh.size() > 8 ? static_cast<unsigned int>(mesh[8]) : 0xFFFFFFFFu;    // ... my Q-like data
   TORCH_CHECK(qlike.size() <= 2 && kvlike.size() <= 2 && qlike.size() == q_offs.size() && kvlike.size() == kv_offs.size() &&
               !kvlike.empty(), "push tensor lists");
   const at::Tensor& k0 = kvlike[0];

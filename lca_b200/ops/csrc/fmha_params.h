@@ -74,6 +74,8 @@ struct CommParams {
   long long stage_q_rows, stage_kv_rows;   // rows of the staging tensors (S/R and S)
   unsigned int epoch;                // 1-based call counter
   unsigned int o_target;             // value kSigODone must reach before this rank's kernel may exit (0: skip)
+  unsigned int kv_dst_mask, q_dst_mask;   // bit d: sp-rank d needs the DATA of my KV-like / Q-like tensors (its arrival
+                                     // counters are bumped either way); causal / windowed layouts leave most peers out
   int push_mode;                     // 1: TMA bulk-copy push engine (default), 0: scalar st.global loop (LCA_B200_PUSH=scalar)
   unsigned long long watchdog_ns;    // spin-wait budget before the kernel traps (LCA_B200_WATCHDOG_S, 0 = wait forever)
 };

@@ -99,14 +99,14 @@ static __device__ __noinline__ void comm_cta(const CommParams& c, bool wait_o) {
     m.row_vecs = c.Hkvl * c.D * esz / 16;
     m.dst_ss = static_cast<long long>(c.Hkvl) * c.D * esz;
     m.dst_sb = c.stage_kv_rows * m.dst_ss;
-    for (int t = 0; t < c.n_kv; ++t) {
+    for (int t = 0; t < c.n_kv && ((c.kv_dst_mask >> d) & 1u); ++t) {
       m.src = static_cast<const unsigned char*>(c.kvt[t].src) + static_cast<long long>(h0) * c.D * esz;
       m.src_sb = c.kvt[t].sb * esz; m.src_ss = c.kvt[t].ss * esz;
       m.dst = c.peer_slab[d] + c.kvt[t].off + row_off_kv * m.dst_ss;
       comm_copy(m, c.B, tid, nthreads);
     }
     const bool have_q = c.n_q > 0 || c.n_stat > 0;
-    const bool send_q = have_q && (c.q_to_all || dr == c.r);
+    const bool send_q = have_q && (c.q_to_all || dr == c.r) && ((c.q_dst_mask >> d) & 1u);
     if (send_q) {
       const long long q_rows = c.q_to_all ? c.stage_kv_rows : c.stage_q_rows;     // rows of the destination staging
       const long long q_off = c.q_to_all ? row_off_kv : row_off_q;
@@ -297,9 +297,13 @@ static __device__ __noinline__ void comm_cta_bulk(const CommParams& c, uint32_t 
       const int du = d % c.U, dr = d / c.U;
       const bool do_kv = sweep == 0;
       const bool do_q = have_q && (c.q_to_all ? sweep == 1 : dr == c.r);
+      // destinations whose tiles can never see these rows (causal order, sliding window) get the arrival signal
+      // but no data: the consumers' tile iterators skip exactly those segments (host: FusedUSPEngine._push_masks)
+      const bool kv_data = do_kv && ((c.kv_dst_mask >> d) & 1u);
+      const bool q_data = do_q && ((c.q_dst_mask >> d) & 1u);
       BulkMsg msgs[6];
       int n_msg = 0, total = 0;
-      if (do_q) {                                   // forward: the consumer needs its Q tile before any K/V tile
+      if (q_data) {                                   // forward: the consumer needs its Q tile before any K/V tile
         const long long q_rows = c.q_to_all ? c.stage_kv_rows : c.stage_q_rows;     // rows of the destination staging
         const long long q_off = c.q_to_all ? row_off_kv : row_off_q;
         for (int t = 0; t < c.n_q; ++t) {
@@ -328,7 +332,7 @@ static __device__ __noinline__ void comm_cta_bulk(const CommParams& c, uint32_t 
           total += m.nchunks;
         }
       }
-      if (do_kv) {
+      if (kv_data) {
         const int h0 = (c.Hkv >= c.U) ? du * c.Hkvl : (du * c.Hkv) / c.U;      // kv head(s) of destination du
         for (int t = 0; t < c.n_kv; ++t) {
           BulkMsg& m = msgs[n_msg++];

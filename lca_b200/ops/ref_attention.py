@@ -60,6 +60,12 @@ def _expand_kv(x: torch.Tensor, H: int) -> torch.Tensor:
     return x.repeat_interleave(H // Hkv, dim=2)
 
 
+def _bounded_chunk(q_chunk: int, B: int, H: int, Sk: int, budget_elems: int = 1 << 28) -> int:
+    """Query rows per step such that one (B, H, rows, Sk) fp32 temporary stays under ~1 GiB: the engine's memory is
+    O(rows * Sk), never O(Sq * Sk) -- head dims the tcgen05 kernels do not take (> 128) stay usable at long context."""
+    return max(16, min(q_chunk, budget_elems // max(1, B * H * Sk)))
+
+
 def attn_block_fwd_ref(
     q: torch.Tensor,
     k: torch.Tensor,
@@ -80,6 +86,7 @@ def attn_block_fwd_ref(
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     dev = q.device
+    q_chunk = _bounded_chunk(q_chunk, B, H, Sk)
     kf = _expand_kv(k, H).to(torch.float32).permute(0, 2, 3, 1)  # (B,H,D,Sk)
     vf = _expand_kv(v, H).to(torch.float32).permute(0, 2, 1, 3)  # (B,H,Sk,D)
     out = torch.empty(B, Sq, H, D, dtype=q.dtype, device=dev)
@@ -138,6 +145,7 @@ def attn_block_bwd_ref(
     Sk, Hkv = k.shape[1], k.shape[2]
     dev = q.device
     g = H // Hkv
+    q_chunk = _bounded_chunk(q_chunk, B, H, Sk)
     kf = _expand_kv(k, H).to(torch.float32).permute(0, 2, 1, 3)   # (B,H,Sk,D)
     vf = _expand_kv(v, H).to(torch.float32).permute(0, 2, 1, 3)
     dq = torch.zeros(B, Sq, H, D, dtype=torch.float32, device=dev)

@@ -176,6 +176,7 @@ class FusedUSPEngine:
         # N=2: 8 -> 16 CTAs: forward 2064 -> 2098 TFLOPS, Ulysses S=32K forward 5.8 -> 5.1 ms)
         self.n_comm = int(os.environ.get("LCA_B200_COMM_CTAS", "16"))
         self._plan = {}                         # call shape -> kv heads per launch (0 = refused), decided collectively, once
+        self._segs = {}                         # (builder, args) -> marshalled segment lists of the current slab layout
         self.slab_bytes = 0
         self.with_bwd = os.environ.get("LCA_B200_FUSED_BWD", "1") == "1"
         # the signal pad lives in its own small slab so that growing the data slab never resets counters
@@ -325,6 +326,7 @@ class FusedUSPEngine:
         self.off_lse_own, self.off_do, self.off_delta = offs["lse_own"], offs["do"], offs["delta"]
         self.off_lse2, self.off_dk, self.off_dv = offs["lse2"], offs["dk"], offs["dv"]
         self.key = key
+        self._segs.clear()                      # segment lists embed peer pointers + offsets of the layout
         self.slab_bytes = self.slab.nbytes
 
     def dropout_seed(self) -> int:
@@ -378,9 +380,10 @@ class FusedUSPEngine:
         else:
             o_target = 0
         self._arm_dropout(p, Hl)
+        kvm, qm = self._push_masks(variant, rows, p, cu, False)
         C.usp_fwd(qst, kst, vst, q, k, v, qsegs, ksegs, qstride, qstride, out_local, u * Hl, lse,
                   float(p.softmax_scale), wl, wr, float(p.softcap), alibi,
-                  [P, U, R, u, r, rows, self.n_comm],
+                  [P, U, R, u, r, rows, self.n_comm, kvm, qm],
                   [self.off_q, self.off_k, self.off_v, Sr, P * rows],
                   slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, o_target)
         if push_q:   # the symmetric buffers are reused by the next call
@@ -409,7 +412,67 @@ class FusedUSPEngine:
             raise ValueError(f"cu_seqlens ends at {int(cu[-1])} but the local shard has {rows} tokens")
         return lambda rr: varlen_positions(variant, rr, self.R, cu)
 
+    def _push_masks(self, variant, rows, p: AttnParams, cu, backward: bool):
+        """-> (kv_mask, q_mask): bit d set iff sp-rank d needs the DATA of my K/V rows / my Q-like rows.  Under a causal
+        or sliding-window mask most (source, destination) pairs never meet (basic causal ring: rank d never reads keys
+        of later ranks; window 8K at S=128K: only neighbours): the push CTAs still bump those destinations' arrival
+        counters (the epochs stay aligned) but move no bytes.  Sound because the consumers' tile iterators visit a
+        segment only if some tile of it is visible under the very same bounds (``native.window_bounds``), tested here
+        on whole segments.  Destinations in my own ring block always get everything (their stationary operands)."""
+        P, U, u, r = self.P, self.U, self.u, self.r
+        every = (1 << P) - 1
+        if not p.causal and tuple(p.window_size) == (-1, -1):
+            return every, every
+        key = ("m", variant, rows, cu, bool(p.causal), tuple(p.window_size), backward)
+        hit = self._segs.get(key)
+        if hit is not None:
+            return hit
+        pos_of = self._pos_of(variant, rows, cu)
+        mine = tuple(sg for sg, _ in _slices_with_rows(pos_of(r), u * rows, (u + 1) * rows))
+        wl, wr = native.window_bounds(p)           # the kernels' own bounds: visible iff -wl <= kpos - qpos <= wr
+
+        def sees(qsegs, ksegs) -> bool:            # segment-pair granularity (a zigzag shard is two far-apart chunks)
+            for a in qsegs:
+                for b in ksegs:
+                    if a.group != b.group or a.count == 0 or b.count == 0:
+                        continue
+                    qlo, qhi = a.start, a.start + (a.count - 1) * a.stride
+                    klo, khi = b.start, b.start + (b.count - 1) * b.stride
+                    if (wr >= 0 and klo - qhi > wr) or (wl >= 0 and qlo - khi > wl):
+                        continue
+                    return True
+            return False
+
+        kv_mask = q_mask = 0
+        for d in range(P):
+            dr = d // U
+            blk = pos_of(dr)                       # queries (dQ pass / forward) and keys (dK/dV pass) of d's ring block
+            if dr == r or sees(blk, mine):
+                kv_mask |= 1 << d
+            if not backward or dr == r or sees(mine, blk):
+                q_mask |= 1 << d
+        self._segs[key] = (kv_mask, q_mask)
+        return kv_mask, q_mask
+
+    def _cached(self, name, fn, *args):
+        """Segment lists are pure functions of (mesh, layout, variant, rows, cu): built once per call shape, not per
+        call (the marshalling was a visible part of the step at the 4K-32K sequence lengths of BASELINE config 2)."""
+        key = (name,) + tuple(tuple(a) if isinstance(a, list) else a for a in args)
+        hit = self._segs.get(key)
+        if hit is None:
+            hit = self._segs[key] = fn(*args)
+        return hit
+
     def _q_segments(self, variant, rows, pushed: bool, off_out: int, off_lse=None, cu=None):
+        return self._cached("q", self._q_segments_build, variant, rows, pushed, off_out, off_lse, cu)
+
+    def _k_segments(self, variant, rows, cu=None):
+        return self._cached("k", self._k_segments_build, variant, rows, cu)
+
+    def _bwd_segments(self, variant: str, rows: int, cu=None):
+        return self._cached("b", self._bwd_segments_build, variant, rows, cu)
+
+    def _q_segments_build(self, variant, rows, pushed: bool, off_out: int, off_lse=None, cu=None):
         """Rows of my gathered Q (ring rank r) split by source shard -> kernel q segments
         [row0, nrows, pos0, flag, o_row0, o_base, o_sig, group]; also the number of 128-row tiles over MY rows."""
         U, R, u, r = self.U, self.R, self.u, self.r
@@ -433,7 +496,7 @@ class FusedUSPEngine:
         segs.sort(key=lambda x: -x[2])          # heaviest (latest positions) first
         return segs, n_my_tiles
 
-    def _k_segments(self, variant, rows, cu=None):
+    def _k_segments_build(self, variant, rows, cu=None):
         """All K/V rows in my staging (every source shard) -> [row0, nrows, pos0, flag, group], own block first."""
         U, R, u, r = self.U, self.R, self.u, self.r
         Sr = U * rows
@@ -447,7 +510,7 @@ class FusedUSPEngine:
                     segs.append([sr * Sr + row0, s.count, s.start, SIG_KV + sr * U + su, s.group])
         return segs
 
-    def _bwd_segments(self, variant: str, rows: int, cu=None):
+    def _bwd_segments_build(self, variant: str, rows: int, cu=None):
         """Every token shard of the mesh as a segment list over the (B, S, ...) all-rank staging layout of the
         owner-computes backward -> (all_segs, mine, tiles_of_me); a segment is (src sp-rank, staging row0, nrows,
         global position of its first token, attention group).  ``mine`` = segments of my ring block (the stationary
@@ -517,9 +580,10 @@ class FusedUSPEngine:
                self.sig.peer_ptrs[src] + 4 * SIG_ODONE] for (src, row0, n, pos0, grp) in sorted(mine, key=lambda t: -t[3])]
         self.o_total += U * B * Hl * tiles_of_me * 2
         self._arm_dropout(p, Hl)
+        kvm, qm = self._push_masks(variant, rows, p, cu, True)
         C.usp_bwd_pass(False, q_all, do_all, kst, vst, xq, ksegs, stride, stride, lse2_all, delta_all, dq_own, None, 0,
                        u * Hl, float(p.softmax_scale), wl, wr, float(p.softcap), alibi, self.sig.ptr, fe,
-                       [P, U, R, u, r, rows, self.n_comm], [q, dout], [self.off_q, self.off_do], [k, v],
+                       [P, U, R, u, r, rows, self.n_comm, kvm, qm], [q, dout], [self.off_q, self.off_do], [k, v],
                        [self.off_k, self.off_v], [delta_local, lse2_local], [self.off_delta, self.off_lse2], True, Sr, S,
                        slab.peer_ptrs, self.sig.peer_ptrs, self.sig.ptr, self.epoch, self.o_total & 0xFFFFFFFF, H, Hkv)
         # ---- pass 2: dK/dV of my ring block's keys (stationary) against EVERY rank's queries (streamed)
@@ -579,7 +643,8 @@ class FusedUSPEngine:
             o_target = self.o_total & 0xFFFFFFFF
         else:
             o_target = 0
-        mesh = [P, U, R, u, r, rows, self.n_comm]
+        kvm, _ = self._push_masks(variant, rows, p, cu, False)      # Q-like tensors only go to my own ring block here
+        mesh = [P, U, R, u, r, rows, self.n_comm, kvm, (1 << P) - 1]
         ql, qo = ([q, dout], [self.off_q, self.off_do]) if pushed else ([], [])
         self._arm_dropout(p, Hl)
         C.usp_bwd_pass(False, qst, dost, kst, vst, xq, ksegs, stride, stride, lse2, delta_c, dq_local, None, 0, u * Hl,

@@ -202,6 +202,8 @@ CASES = {
         C("r2_zigzag_gqa", 1, 2, "zigzag", 4, 2, 2048, 128),
         C("r2_stripe_window_d64", 1, 2, "stripe", 2, 2, 1024, 64, dict(causal=True, window_size=(300, 0))),
         C("r2_basic_noncausal", 1, 2, "basic", 2, 2, 1024, 128, dict(causal=False)),
+        # causal basic ring: the push CTAs leave out destinations that can never see the rows (signal without data)
+        C("r2_basic_causal", 1, 2, "basic", 4, 2, 2048, 128),
         C("u2_ulysses_module_gqa", 2, 1, "basic", 8, 2, 1024, 128, module="ulysses"),
         C("u2_mqa_softcap", 2, 1, "basic", 4, 1, 512, 128, dict(causal=True, softcap=10.0)),
         C("u2_mqa", 2, 1, "basic", 4, 1, 1024, 128),
@@ -228,6 +230,8 @@ CASES = {
         C("u2r2_stripe_d64", 2, 2, "stripe", 4, 4, 2048, 64),
         C("u4_mqa", 4, 1, "basic", 8, 2, 2048, 128),
         C("u2r2_batch2", 2, 2, "zigzag", 4, 2, 2048, 128, B=2),
+        C("r4_basic_causal_window", 1, 4, "basic", 4, 2, 4096, 128, dict(causal=True, window_size=(600, 0))),
+        C("u2r2_basic_causal", 2, 2, "basic", 4, 2, 2048, 128),
         # use_ulysses_low=False: ring groups on the contiguous ranks (reference globals.py:59-78)
         C("u2r2_ulysses_high", 2, 2, "zigzag", 4, 2, 2048, 128, ulysses_low=False),
         C("u2r2_ulysses_high_headgroups", 2, 2, "zigzag", 8, 4, 2048, 128, ulysses_low=False, env={"LCA_B200_HEAD_CHUNK": "2"}),
@@ -242,6 +246,7 @@ CASES = {
         C("u2r4_stripe", 2, 4, "stripe", 4, 4, 8192, 128),
         C("u8_mqa", 8, 1, "basic", 16, 2, 8192, 128),
         C("u2r4_batch2", 2, 4, "zigzag", 8, 4, 4096, 128, B=2),
+        C("r8_basic_causal_window", 1, 8, "basic", 4, 2, 8192, 128, dict(causal=True, window_size=(1500, 0))),
         C("u4r2_ulysses_high", 4, 2, "zigzag", 16, 8, 8192, 128, ulysses_low=False),
         C("r8_zigzag_256k", 1, 8, "zigzag", 2, 1, 262144, 128, kind="long"),
     ],

@@ -20,6 +20,7 @@ def _engine(U, R, u, r):
     e = object.__new__(FusedUSPEngine)
     e.U, e.R, e.u, e.r, e.P, e.me = U, R, u, r, U * R, r * U + u
     e.slab, e.sig = _FakeSlab(U * R), _FakeSlab(U * R)
+    e._segs = {}
     return e
 
 
@@ -265,3 +266,43 @@ def test_ulysses_high_mesh_permutes_only_the_pointer_tables(U, R):
         for r in range(R):
             for u in range(U):
                 assert table[r * U + u] == coords_to_rank(u, r, 0, U, R, low)
+
+
+@pytest.mark.parametrize("U,R", [(1, 4), (2, 2), (2, 4), (1, 8)])
+@pytest.mark.parametrize("variant", ["basic", "zigzag", "stripe"])
+@pytest.mark.parametrize("window", [(-1, -1), (24, 0)])
+def test_push_masks_never_leave_out_a_needed_destination(U, R, variant, window):
+    """Destination masks of the push CTAs: a bit may only be clear if NO (query of the destination's ring block, key of
+    my shard) pair -- resp. (my query, key of its ring block) for the backward -- is visible under the exact mask; and a
+    causal basic ring must actually skip the later-to-earlier direction."""
+    P, rows = U * R, 16
+    S = P * rows
+    q = torch.zeros(1, S, 1, 8)
+    p = AttnParams.make(q, None, True, window)
+    own = {(su, sr): local_token_index(variant, S, su, sr, U, R) for su in range(U) for sr in range(R)}
+    blk = {sr: torch.cat([own[(su, sr)] for su in range(U)]) for sr in range(R)}
+    wl = window[0]
+
+    def visible(qpos, kpos):
+        rel = kpos.view(1, -1) - qpos.view(-1, 1)
+        ok = rel <= 0
+        if wl >= 0:
+            ok &= rel >= -wl
+        return bool(ok.any())
+
+    skipped = 0
+    for r in range(R):
+        for u in range(U):
+            e = _engine(U, R, u, r)
+            for backward in (False, True):
+                kvm, qm = e._push_masks(variant, rows, p, None, backward)
+                for d in range(P):
+                    dr = d // U
+                    if not (kvm >> d) & 1:
+                        skipped += 1
+                        assert dr != r and not visible(blk[dr], own[(u, r)])
+                    if not (qm >> d) & 1:
+                        skipped += 1
+                        assert backward and dr != r and not visible(own[(u, r)], blk[dr])
+    if variant == "basic" and R > 1:
+        assert skipped > 0
