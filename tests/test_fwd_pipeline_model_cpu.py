@@ -1,6 +1,7 @@
 """Executable model of the barrier protocol of ``csrc/fmha_fwd_sm100.cu`` (one 128-column score buffer per Q tile,
-tensor-pipe order ``QK0(j+1) | PV1(j) | QK1(j+1) | PV0(j+1)``, 5-slot K/V ring), in the form the opt-in variants use
-(``kQf``: empty work items are handed back through ``o_full``).  Same construction as the backward model."""
+tensor-pipe order ``QK0(j+1) | PV1(j) | QK1(j+1) | PV0(j+1)``, 5-slot K/V ring); empty work items are handed back
+through ``o_full`` (``qf=True``, what every instantiation does since round 2; ``qf=False`` is the round-1 rule, kept as the
+negative control).  Same construction as the backward model."""
 import queue
 import random
 import threading
