@@ -45,7 +45,8 @@ def make_varlen(variant: str, with_half_index: bool):
     the reference threads two precomputed index tensors through (``half_index0/1``); they are accepted and ignored --
     positions make them unnecessary."""
 
-    def forward(process_group, q, k, v, cu_seqlens, max_seqlen, *rest, **kw):
+    def parse(q, rest, kw):
+        """Positional tail / keywords of the reference's low-level signature -> (q as a batch of one, AttnParams, args)."""
         if with_half_index:
             rest = rest[2:] if len(rest) >= 2 else rest
             kw.pop("half_index0", None), kw.pop("half_index1", None)
@@ -56,6 +57,10 @@ def make_varlen(variant: str, with_half_index: bool):
         q4 = q.unsqueeze(0)
         p = _params(q4, a["softmax_scale"], a["causal"], a["window_size"], a["softcap"], a["alibi_slopes"],
                     a["dropout_p"], a["deterministic"])
+        return q4, p, a
+
+    def forward(process_group, q, k, v, cu_seqlens, max_seqlen, *rest, **kw):
+        q4, p, a = parse(q, rest, kw)
         if p.dropout_p > 0:
             raise NotImplementedError("dropout is not supported on the varlen ring path")
         cu = _cu_list(cu_seqlens)
@@ -64,16 +69,7 @@ def make_varlen(variant: str, with_half_index: bool):
         return out.squeeze(0), lse.squeeze(0)
 
     def backward(process_group, dout, q, k, v, out, softmax_lse, cu_seqlens, max_seqlen, *rest, **kw):
-        if with_half_index:
-            rest = rest[2:] if len(rest) >= 2 else rest
-            kw.pop("half_index0", None), kw.pop("half_index1", None)
-        names = ["softmax_scale", "dropout_p", "causal", "window_size", "softcap", "alibi_slopes", "deterministic"]
-        a = dict(dropout_p=0, causal=True, window_size=(-1, -1), softcap=0.0, alibi_slopes=None, deterministic=False)
-        a.update(dict(zip(names, rest)))
-        a.update(kw)
-        q4 = q.unsqueeze(0)
-        p = _params(q4, a["softmax_scale"], a["causal"], a["window_size"], a["softcap"], a["alibi_slopes"],
-                    a["dropout_p"], a["deterministic"])
+        q4, p, a = parse(q, rest, kw)
         cu = _cu_list(cu_seqlens)
         dq, dk, dv = ring_attn_backward(process_group, dout.unsqueeze(0), q4, k.unsqueeze(0), v.unsqueeze(0),
                                         out.unsqueeze(0), softmax_lse.unsqueeze(0), variant, p,
