@@ -306,3 +306,40 @@ def test_push_masks_never_leave_out_a_needed_destination(U, R, variant, window):
                         assert backward and dr != r and not visible(own[(u, r)], blk[dr])
     if variant == "basic" and R > 1:
         assert skipped > 0
+
+
+def test_head_group_launches_equal_one_launch(monkeypatch):
+    """``FusedUSPEngine.attention`` with ``kv_heads_per_launch < Hkv``: the per-group slices of q / k / v / ALiBi slopes
+    and the concatenation of outputs and LSE must reproduce the single-launch result (GQA groups stay aligned, the
+    dropout head offset of a group is its first global query head).  The kernel launch is replaced by the PyTorch engine."""
+    from lca_b200.parallel import fused_engine as fe
+    from lca_b200.ops.attention import attn_block_fwd
+    from lca_b200.parallel.layout import Seg
+
+    seen = []
+
+    def fake_apply(q, k, v, eng, variant, p, cu):
+        seen.append((q.shape[2], k.shape[2], int(p.head_offset), None if p.alibi_slopes is None else p.alibi_slopes.clone()))
+        pos = (Seg(0, q.shape[1], 1),)
+        return attn_block_fwd(q, k, v, pos, pos, p, "torch")
+
+    monkeypatch.setattr(fe._FusedAttnFunc, "apply", staticmethod(fake_apply))
+    e = _engine(1, 2, 0, 0)
+    g = torch.Generator().manual_seed(3)
+    B, S, H, Hkv, D = 2, 48, 8, 4, 16
+    q, k, v = (torch.randn(B, S, h, D, generator=g) for h in (H, Hkv, Hkv))
+    slopes = torch.tensor([2.0 ** -(i + 1) for i in range(H)])
+    kw = dict(softmax_scale=None, causal=True, window_size=(-1, -1), softcap=0.0, alibi_slopes=slopes, deterministic=False)
+    whole, lse_w = fe.FusedUSPEngine.attention(e, q, k, v, "zigzag", return_lse=True, **kw)
+    assert [s[:3] for s in seen] == [(8, 4, 0)]
+    seen.clear()
+    parts, lse_p = fe.FusedUSPEngine.attention(e, q, k, v, "zigzag", return_lse=True, kv_heads_per_launch=1, **kw)
+    assert [s[:2] for s in seen] == [(2, 1)] * 4
+    for i, s in enumerate(seen):
+        torch.testing.assert_close(s[3], slopes[2 * i:2 * i + 2])
+    torch.testing.assert_close(parts, whole)
+    torch.testing.assert_close(lse_p, lse_w)
+    seen.clear()
+    fe.FusedUSPEngine.attention(e, q, k, v, "zigzag", kv_heads_per_launch=2, dropout_p=0.25, dropout_seed=7,
+                                **{**kw, "alibi_slopes": None})
+    assert [s[:3] for s in seen] == [(4, 2, 0), (4, 2, 4)]            # head offsets = first global query head of the group
