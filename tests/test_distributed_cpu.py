@@ -339,3 +339,44 @@ def _lowlevel_worker(rank, world):
 
 def test_reference_module_paths_and_lowlevel_ring_functions():
     run_distributed(_lowlevel_worker, 2)
+
+
+def _slab_plan_worker(rank, world):
+    """Ranks with DIFFERENT memory caps must take the same plan (the smallest), and a call that fits nowhere must be
+    refused on every rank (collective fallback), decided once per call shape."""
+    import types
+    from lca_b200.parallel.fused_engine import FusedUSPEngine, _SlabDoesNotFit
+    e = object.__new__(FusedUSPEngine)
+    e.U, e.R, e.P, e.u, e.r, e.me = 1, world, world, 0, rank, rank
+    e.group, e.device = None, torch.device("cpu")
+    e.with_bwd, e._plan, e.slab, e.slab_bytes = True, {}, None, 0
+    ensured = []
+    e._ensure = types.MethodType(lambda self, *key: ensured.append(key), e)
+    B, rows, H, Hkv, D = 1, 4096, 16, 8, 128
+    q, k = torch.empty(B, rows, H, D, dtype=torch.bfloat16), torch.empty(B, rows, Hkv, D, dtype=torch.bfloat16)
+    full = e.staging_bytes(B, rows, H, Hkv, D, 2, True)
+    caps = [full + 1, full // 3][rank % 2]                     # rank 0 could take the whole call, rank 1 only a quarter of the heads
+    e._cap_bytes = types.MethodType(lambda self: caps, e)
+    c = e.reserve(q, k, True)
+    assert c == 2, c                                            # 8 kv heads -> groups of 2 fit under a third of the slab
+    assert ensured == [(B, rows, H // Hkv * 2, 2, D, 2, True)]
+    assert e.reserve(q, k, True) == 2 and len(ensured) == 1     # cached: no second collective, no second layout
+    # forward-only calls are planned separately (smaller layout: K/V + my ring block's Q)
+    assert e.reserve(q, k, False) in (8, 4, 2)
+    # nothing fits on one rank -> refused everywhere
+    e._plan.clear()
+    tiny = [full, 1024][rank % 2]
+    e._cap_bytes = types.MethodType(lambda self: tiny, e)
+    assert e.reserve(q, k, True) == 0
+    # allocation failure after a positive plan -> refused as well
+    e._plan.clear()
+    e._cap_bytes = types.MethodType(lambda self: full + 1, e)
+
+    def boom(self, *key):
+        raise _SlabDoesNotFit("no memory")
+    e._ensure = types.MethodType(boom, e)
+    assert e.reserve(q, k, True) == 0
+
+
+def test_fused_slab_plan_is_agreed_across_ranks():
+    run_distributed(_slab_plan_worker, 2)
