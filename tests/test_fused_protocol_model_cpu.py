@@ -7,8 +7,10 @@ Each rank runs its kernels in stream order; inside a kernel a push thread (the c
 attention CTAs) run concurrently, and the ranks drift apart at random.  Staging buffers carry the epoch of their
 contents: a reader must find exactly the current call's data (never a stale or a too-new version), i.e. the model checks
 that no rank can overwrite a peer's staging while that peer may still read the previous contents, and that nothing
-deadlocks.  Both push flavours are modelled: the unicast loop and the NVLS-style broadcast (wait for ALL ready flags,
-one write, then all arrival counters)."""
+deadlocks.  Destination masks are modelled too (round 2): under a causal / window mask a source sends a destination the
+arrival SIGNAL but no data -- and does not wait for its ready-to-receive flag -- while the consumer never visits those
+segments; the set of skipped pairs changes from call to call (layers with different masks), so the monotonic counters
+must stay aligned.  (The NVLS-style broadcast push of round 1 is gone from the kernels and from the model.)"""
 import random
 import threading
 import time
@@ -43,10 +45,12 @@ class Sig:
 
 
 class Mesh:
-    def __init__(self, U, R, n_comm, broadcast, seed, use_rtr=True, slow_reader=None):
+    def __init__(self, U, R, n_comm, seed, use_rtr=True, slow_reader=None, masked=False, signal_skipped=True):
         self.slow_reader = slow_reader              # (rank, seconds): that rank dwells on every staging read
-        self.U, self.R, self.P, self.n_comm, self.broadcast = U, R, U * R, n_comm, broadcast
+        self.U, self.R, self.P, self.n_comm = U, R, U * R, n_comm
         self.use_rtr = use_rtr
+        self.masked = masked                        # destination masks that differ from call to call
+        self.signal_skipped = signal_skipped        # False = the bug the kernels must not have (negative control)
         self.rng = random.Random(seed)
         self.sig = [Sig() for _ in range(self.P)]
         self.lock = threading.Lock()
@@ -63,6 +67,14 @@ class Mesh:
             self.errors.append(msg)
             raise AssertionError(msg)
 
+    def needs_data(self, epoch, src, dst) -> bool:
+        """Does `dst` ever visit rows of `src` in call `epoch`?  Ranks of the same ring block always do (stationary
+        operands); otherwise a call-dependent pseudo-random subset (every rank evaluates the same function, like the
+        engines evaluate the same mask)."""
+        if not self.masked or src // self.U == dst // self.U:
+            return True
+        return (epoch * 7 + src * 3 + dst) % 3 != 0
+
     # ------------------------------------------------------------------ one kernel on one rank
     def push(self, me, epoch, classes_all, classes_ring):
         """comm CTAs: classes_all go to every rank, classes_ring (Ulysses Q) to the ranks of my ring index."""
@@ -70,28 +82,19 @@ class Mesh:
         for t in range(self.P):
             self.sig[t].store_max(RTR + me, epoch)                    # my staging is free for this call
         order = [(me + i) % self.P for i in range(self.P)]
-        if self.broadcast and self.U == 1:
-            for d in order:
+        for d in order:
+            if self.needs_data(epoch, me, d):
                 if self.use_rtr:
                     self.sig[me].wait_ge(RTR + d, epoch)
-            self.jitter()
-            with self.lock:
-                for d in range(self.P):
+                self.jitter()
+                with self.lock:
                     for c in classes_all:
                         self._write(d, (c, me), epoch)
-            for d in order:
-                self._signal(d, me, u, d // self.U == r)
-            return
-        for d in order:
-            if self.use_rtr:
-                self.sig[me].wait_ge(RTR + d, epoch)
-            self.jitter()
-            with self.lock:
-                for c in classes_all:
-                    self._write(d, (c, me), epoch)
-                if d // self.U == r:
-                    for c in classes_ring:
-                        self._write(d, (c, me), epoch)
+                    if d // self.U == r:
+                        for c in classes_ring:
+                            self._write(d, (c, me), epoch)
+            elif not self.signal_skipped:
+                continue
             self._signal(d, me, u, d // self.U == r)
 
     def _write(self, dst, key, epoch):
@@ -156,44 +159,73 @@ class Mesh:
             # forward: K/V to everyone, Q to my Ulysses peers; I read Q of my ring block and every K/V
             epoch += 1
             needs = ([(Q + x, ("q", r * U + x)) for x in range(U)] if U > 1 else []) + \
-                    [(KV + s, ("kv", s)) for s in [(me + i) % P for i in range(P)]]
+                    [(KV + s, ("kv", s)) for s in [(me + i) % P for i in range(P)] if self.needs_data(epoch, s, me)]
             if U > 1:
                 o_total += U
             self.kernel(me, epoch, ["kv"], ["q"] if U > 1 else [], needs, ring_block if U > 1 else [], ODONE,
                         o_total if U > 1 else None)
             # backward, dQ pass: q/dO/stats and K/V to EVERY rank; dQ tiles go to the owners in my ring block
             epoch += 1
-            needs = [(QA + s, ("qa", s)) for s in ring_block] + [(KV + s, ("kv", s)) for s in range(P)]
+            needs = [(QA + s, ("qa", s)) for s in ring_block] + \
+                    [(KV + s, ("kv", s)) for s in range(P) if self.needs_data(epoch, s, me)]
             o_total += U
             self.kernel(me, epoch, ["kv", "qa"], [], needs, ring_block, ODONE, o_total)
             # backward, dK/dV pass: no comm role; reads what pass 1 delivered; dK/dV tiles go to the owners
-            needs = [(KV + s, ("kv", s)) for s in ring_block] + [(QA + s, ("qa", s)) for s in range(P)]
+            needs = [(KV + s, ("kv", s)) for s in ring_block] + \
+                    [(QA + s, ("qa", s)) for s in range(P) if self.needs_data(epoch, s, me)]
             dkv_total += U
             self.kernel(me, epoch, [], [], needs, ring_block, DKV, dkv_total)    # target = the host's symm_wait
 
 
-@pytest.mark.parametrize("U,R", [(1, 2), (2, 1), (2, 2), (1, 8), (4, 2)])
-@pytest.mark.parametrize("broadcast", [False, True])
-def test_fused_cross_rank_protocol(U, R, broadcast):
-    if broadcast and U != 1:
-        pytest.skip("the broadcast push exists for pure-ring meshes only")
-    mesh = Mesh(U, R, n_comm=2, broadcast=broadcast, seed=U * 10 + R)
+def _run_mesh(mesh, steps, join=120):
     res = {}
 
     def guard(me):
         try:
-            mesh.rank(me, steps=3)
+            mesh.rank(me, steps=steps)
         except Exception as e:  # noqa: BLE001
             res[me] = e
 
-    threads = [threading.Thread(target=guard, args=(me,), daemon=True) for me in range(U * R)]
+    threads = [threading.Thread(target=guard, args=(me,), daemon=True) for me in range(mesh.P)]
     for t in threads:
         t.start()
     for t in threads:
-        t.join(120)
+        t.join(join)
         assert not t.is_alive(), f"deadlock: {res}"
+    return res
+
+
+@pytest.mark.parametrize("U,R", [(1, 2), (2, 1), (2, 2), (1, 8), (4, 2)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_fused_cross_rank_protocol(U, R, masked):
+    mesh = Mesh(U, R, n_comm=2, seed=U * 10 + R, masked=masked)
+    res = _run_mesh(mesh, steps=3)
     assert not res, res
     assert not mesh.errors, mesh.errors
+
+
+def test_model_detects_a_skipped_destination_that_gets_no_signal():
+    """Negative control for the destination masks: if a source skipped the arrival signal together with the data, its
+    counter would lag one call behind for ever and the next call that does need its rows would wait for ever."""
+    Sig.TIMEOUT = 2.0
+    try:
+        mesh = Mesh(1, 4, n_comm=2, seed=5, masked=True, signal_skipped=False)
+        res = {}
+
+        def guard(me):
+            try:
+                mesh.rank(me, steps=3)
+            except Exception as e:  # noqa: BLE001
+                res[me] = e
+
+        threads = [threading.Thread(target=guard, args=(me,), daemon=True) for me in range(4)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(60)
+        assert res, "a lagging arrival counter went unnoticed"
+    finally:
+        Sig.TIMEOUT = 20.0
 
 
 def test_model_detects_a_missing_ready_to_receive_handshake():
@@ -202,7 +234,7 @@ def test_model_detects_a_missing_ready_to_receive_handshake():
     Sig.TIMEOUT = 2.0
     try:
         for attempt in range(3):
-            mesh = Mesh(1, 4, n_comm=2, broadcast=False, seed=3 + attempt, use_rtr=False, slow_reader=(0, 0.3))
+            mesh = Mesh(1, 4, n_comm=2, seed=3 + attempt, use_rtr=False, slow_reader=(0, 0.3))
 
             def guard(me):
                 try:
