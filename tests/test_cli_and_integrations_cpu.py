@@ -62,3 +62,15 @@ def test_pipeline_timing_model_reproduces_the_measured_utilisations():
         w = m.solve(lambda x: m.bwd(x, 512, a_dur, False), target)
         assert abs(m.bwd(w, 512, a_dur, False) - target) < 5e-3
         assert m.bwd(w, 512, a_dur, True) > target
+
+
+def test_examples_run_on_cpu_over_gloo():
+    """examples/usp_attention.py: the README's call sequence on two gloo ranks, checked against a single-device run."""
+    import subprocess
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra, port in ((["--ulysses", "1", "--ring-impl", "zigzag"], 29631), (["--ulysses", "2", "--ring-impl", "basic", "--window", "64"], 29632)):
+        r = subprocess.run([_sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(port), os.path.join(root, "examples", "usp_attention.py"), "--device", "cpu",
+                            "--seq", "256", *extra], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "-> OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
