@@ -2,7 +2,7 @@
 //
 //   pass dQ  (kIsDKV = false): stationary X = (Q_i, dO_i) tile of 128 query rows on the TMEM lanes,
 //            streamed   Y = (K_j, V_j) tiles of 64 key rows.
-//              T0 = Q K^T, T1 = dO V^T            (SS MMAs, fp32 in TMEM, double buffered)
+//              T0 = Q K^T, T1 = dO V^T            (SS MMAs, fp32 in TMEM, NS = 2 or 3 stages)
 //              P  = exp2(T0*scale*log2e - lse2_row), dS = P o (T1 - delta_row)   (softmax warpgroups)
 //              dQ += dS K                          (TS MMA: A = dS from TMEM, B = K as MN-major smem)
 //   pass dKV (kIsDKV = true):  stationary X = (K_j, V_j) tile of 128 key rows on the lanes,
@@ -16,7 +16,7 @@
 // the window bounds because rows are keys and columns are queries.
 // Seven GEMMs instead of the five of a fused dQ/dK/dV kernel, but nothing leaves TMEM between
 // them, no fp32 dQ atomics cross L2, and TMEM (512 columns) is never oversubscribed:
-//   [0,128) T0 x2 stages | [128,256) T1 x2 stages | [256,256+D) acc0 | [256+D,256+2D) acc1.
+//   [0, 64 NS) T0 stages | [64 NS, 128 NS) T1 stages | acc0 (D columns) | acc1 (dK/dV pass only); NS: see Cfg.
 //
 // Capability parity: flash_attn::_flash_attn_backward as called from
 // yunchang/kernels/attention.py:205-250 (dq/dk/dv from dout,q,k,v,out,lse).
@@ -44,7 +44,7 @@ constexpr int kTmaWarp = 9;
 // change: tensor pipe 48 % active, issue slots 32 %, i.e. latency-bound, not throughput-bound).
 // dK/dV pass: two accumulators; at D = 128 only NS = 2 stages fit, at D = 64 three do.  (Measured and dropped in
 // round 2: 32-row streamed tiles with NS = 4 -- 5.56 ms against 3.62 ms at S = 32K, the per-tile cost does not shrink
-// with the tile, see profiles/r2/kernel_timings_r2.md.)
+// with the tile, see profiles/README.md section 1.)
 template <int kD, bool kIsDKV, int kBY>
 struct Cfg {
   static constexpr int BY = kBY;                          // streamed rows per tile (TMEM columns of T0/T1)

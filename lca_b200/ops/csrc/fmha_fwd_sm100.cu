@@ -1,6 +1,6 @@
 // Forward flash attention for sm_100a (B200): TMA -> smem -> tcgen05.mma -> TMEM.
 //
-// One persistent CTA per SM, 320 threads, warp-specialised:
+// One persistent CTA per SM, 384 threads (3 warpgroups; warps 10-11 idle), warp-specialised:
 //   warps 0-3  softmax warpgroup for Q tile 0 (one thread per query row; S/P/O live in TMEM)
 //   warps 4-7  softmax warpgroup for Q tile 1
 //   warp  8    MMA issuer (single elected thread issues every tcgen05.mma + tcgen05.commit)
